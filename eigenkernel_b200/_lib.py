@@ -1,0 +1,76 @@
+"""ctypes binding of libekb200.so (the C-ABI of include/ekb200.h).
+
+The product path FAILS LOUDLY when the CUDA library is missing or no GPU is visible: there is no CPU
+fallback (BASELINE.json north_star).  `load()` only dlopens; creating a context needs a GPU.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, byref, c_char, c_char_p, c_double, c_int, c_int32, c_int64, c_uint64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libekb200.so")
+
+_dp = POINTER(c_double)
+
+
+class Ekb200Error(RuntimeError):
+    def __init__(self, fn: str, info: int, text: str = ""):
+        self.fn, self.info = fn, info
+        super().__init__(f"{fn}: info = {info} ({text})")
+
+
+_lib = None
+
+# name -> (argtypes)  ; every function returns int info unless listed in _RESTYPE
+_SIGS = {
+    "ekb200_version": [],
+    "ekb200_create": [POINTER(c_void_p), c_int],
+    "ekb200_destroy": [c_void_p],
+    "ekb200_strerror": [c_int],
+    "ekb200_last_error": [c_void_p],
+    "ekb200_set_option": [c_void_p, c_char_p, c_int64],
+    "ekb200_num_events": [c_void_p],
+    "ekb200_get_event": [c_void_p, c_int, POINTER(c_char_p), POINTER(c_double), POINTER(c_int)],
+    "ekb200_clear_events": [c_void_p],
+    "ekb200_dev_alloc": [c_void_p, c_int64, POINTER(c_void_p)],
+    "ekb200_dev_free": [c_void_p, c_void_p],
+    "ekb200_h2d": [c_void_p, c_void_p, c_void_p, c_int64],
+    "ekb200_d2h": [c_void_p, c_void_p, c_void_p, c_int64],
+    "ekb200_h2d_matrix": [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64],
+    "ekb200_d2h_matrix": [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64],
+    "ekb200_sync": [c_void_p],
+    "ekb200_coo_to_dense": [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64],
+    "ekb200_fill_synthetic": [c_void_p, c_int64, c_uint64, c_double, c_int, c_double, c_void_p, c_int64],
+    "ekb200_dgemm": [c_void_p, c_char, c_char, c_int64, c_int64, c_int64, c_double, c_void_p, c_int64, c_void_p,
+                     c_int64, c_double, c_void_p, c_int64],
+    "ekb200_potrf": [c_void_p, c_int64, c_void_p, c_int64],
+    "ekb200_sygst": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64],
+    "ekb200_trtrs_lt": [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64],
+    "ekb200_measure_fp64_peak": [c_void_p, POINTER(c_double), POINTER(c_double)],
+}
+_RESTYPE = {"ekb200_strerror": c_char_p, "ekb200_last_error": c_char_p}
+
+
+def exported_symbols():
+    """Names every build of libekb200.so must export (= what include/ekb200.h declares)."""
+    return sorted(_SIGS)
+
+
+def load():
+    """dlopen libekb200.so; raises ImportError (loudly) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(make -C eigenkernel_b200/csrc). There is no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in _SIGS.items():
+        f = getattr(lib, name)
+        f.argtypes = argtypes
+        f.restype = _RESTYPE.get(name, c_int)
+    _lib = lib
+    return lib

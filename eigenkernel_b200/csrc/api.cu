@@ -1,0 +1,251 @@
+// Flat C-ABI of libekb200 (declared in include/ekb200.h).
+#include "../../include/ekb200.h"
+
+#include <string.h>
+
+#include "common.cuh"
+
+using namespace ekb;
+
+struct ekb200_ctx {
+  Ctx c;
+  double* invd = nullptr;  // inverted 64x64 diagonal blocks of the current Cholesky factor
+  i64 invd_n = 0;
+};
+
+namespace ekb {
+int measure_fp64_peak(Ctx* ctx, double* dmma_tflops, double* dfma_tflops);
+}
+
+#define CHECK_CTX(h) \
+  if (!(h)) return -1; \
+  Ctx* ctx = &(h)->c; \
+  cudaSetDevice(ctx->device);
+
+static int ensure_invd(ekb200_ctx* h, i64 n) {
+  Ctx* ctx = &h->c;
+  if (h->invd_n >= n && h->invd) return 0;
+  if (h->invd) ctx_free(ctx, h->invd);
+  h->invd = nullptr;
+  h->invd_n = 0;
+  EKB_TRY(ctx_alloc(ctx, (void**)&h->invd, (size_t)cdiv(n, 64) * 64 * 64 * sizeof(double)));
+  h->invd_n = n;
+  return 0;
+}
+
+extern "C" {
+
+int ekb200_version(void) { return 100; }
+
+int ekb200_create(ekb200_ctx** out, int device) {
+  if (!out) return -1;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return EKB_ERR_CUDA;
+  if (device < 0 || device >= ndev) return -2;
+  ekb200_ctx* h = new ekb200_ctx();
+  Ctx* ctx = &h->c;
+  ctx->device = device;
+  if (cudaSetDevice(device) != cudaSuccess) { delete h; return EKB_ERR_CUDA; }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  ctx->num_sms = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return EKB_ERR_CUDA; }
+  if (cudaMalloc((void**)&ctx->d_info, 64 * sizeof(int)) != cudaSuccess) { delete h; return EKB_ERR_NOMEM; }
+  if (cudaMallocHost((void**)&ctx->h_info, 64 * sizeof(int)) != cudaSuccess) { delete h; return EKB_ERR_NOMEM; }
+  *out = h;
+  return 0;
+}
+
+int ekb200_destroy(ekb200_ctx* h) {
+  if (!h) return 0;
+  Ctx* ctx = &h->c;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (void* p : ctx->allocs) cudaFree(p);
+  ctx->allocs.clear();
+  if (ctx->d_info) cudaFree(ctx->d_info);
+  if (ctx->h_info) cudaFreeHost(ctx->h_info);
+  cudaStreamDestroy(ctx->stream);
+  delete h;
+  return 0;
+}
+
+const char* ekb200_strerror(int info) {
+  if (info == 0) return "ok";
+  if (info < 0) return "illegal argument";
+  if (info == EKB_ERR_CUDA) return "CUDA runtime failure";
+  if (info == EKB_ERR_NOMEM) return "device memory allocation failed";
+  if (info == EKB_ERR_INTERNAL) return "internal error";
+  return "numerical failure";
+}
+
+const char* ekb200_last_error(const ekb200_ctx* h) { return h ? h->c.last_error.c_str() : "null context"; }
+
+int ekb200_set_option(ekb200_ctx* h, const char* key, int64_t value) {
+  CHECK_CTX(h);
+  if (!key) return -2;
+  if (!strcmp(key, "band")) {
+    if (value != 32 && value != 64) return -3;
+    ctx->band = (int)value;
+    return 0;
+  }
+  return -2;
+}
+
+int ekb200_num_events(const ekb200_ctx* h) { return h ? (int)h->c.events.size() : 0; }
+int ekb200_get_event(const ekb200_ctx* h, int i, const char** name, double* seconds, int* num_repeated) {
+  if (!h) return -1;
+  if (i < 0 || i >= (int)h->c.events.size()) return -2;
+  const Event& e = h->c.events[i];
+  if (name) *name = e.name.c_str();
+  if (seconds) *seconds = e.seconds;
+  if (num_repeated) *num_repeated = e.num_repeated;
+  return 0;
+}
+int ekb200_clear_events(ekb200_ctx* h) {
+  if (!h) return -1;
+  h->c.events.clear();
+  return 0;
+}
+
+int ekb200_dev_alloc(ekb200_ctx* h, int64_t bytes, void** p) {
+  CHECK_CTX(h);
+  if (bytes < 0) return -2;
+  if (!p) return -3;
+  return ctx_alloc(ctx, p, (size_t)bytes);
+}
+int ekb200_dev_free(ekb200_ctx* h, void* p) {
+  CHECK_CTX(h);
+  cudaStreamSynchronize(ctx->stream);
+  return ctx_free(ctx, p);
+}
+int ekb200_h2d(ekb200_ctx* h, void* dst, const void* src, int64_t bytes) {
+  CHECK_CTX(h);
+  if (bytes < 0) return -4;
+  EKB_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyHostToDevice, ctx->stream));
+  EKB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int ekb200_d2h(ekb200_ctx* h, void* dst, const void* src, int64_t bytes) {
+  CHECK_CTX(h);
+  if (bytes < 0) return -4;
+  EKB_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  EKB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int ekb200_h2d_matrix(ekb200_ctx* h, double* dst, int64_t ldd, const double* src, int64_t lds, int64_t m, int64_t n) {
+  CHECK_CTX(h);
+  if (m < 0 || n < 0) return -6;
+  if (m == 0 || n == 0) return 0;
+  EKB_CUDA(cudaMemcpy2DAsync(dst, ldd * 8, src, lds * 8, m * 8, n, cudaMemcpyHostToDevice, ctx->stream));
+  EKB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int ekb200_d2h_matrix(ekb200_ctx* h, double* dst, int64_t ldh, const double* src, int64_t ldd, int64_t m, int64_t n) {
+  CHECK_CTX(h);
+  if (m < 0 || n < 0) return -6;
+  if (m == 0 || n == 0) return 0;
+  EKB_CUDA(cudaMemcpy2DAsync(dst, ldh * 8, src, ldd * 8, m * 8, n, cudaMemcpyDeviceToHost, ctx->stream));
+  EKB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int ekb200_sync(ekb200_ctx* h) {
+  CHECK_CTX(h);
+  EKB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int ekb200_coo_to_dense(ekb200_ctx* h, int64_t n, int64_t nnz, const int32_t* host_ij, const double* host_v,
+                        double* dev_A, int64_t lda) {
+  CHECK_CTX(h);
+  if (n < 0) return -2;
+  if (nnz < 0) return -3;
+  if (lda < n) return -7;
+  EKB_TRY(set_zero(ctx, dev_A, lda, n, n));
+  if (nnz == 0) return 0;
+  // "last duplicate wins" (distribute_matrix.f90:411-418 executes pdelset sequentially): chunks are
+  // uploaded and scattered in order; inside a chunk duplicates are not expected in symmetric files.
+  int32_t* d_ij = nullptr;
+  double* d_v = nullptr;
+  EKB_TRY(ctx_alloc(ctx, (void**)&d_ij, (size_t)nnz * 2 * sizeof(int32_t)));
+  EKB_TRY(ctx_alloc(ctx, (void**)&d_v, (size_t)nnz * sizeof(double)));
+  EKB_CUDA(cudaMemcpyAsync(d_ij, host_ij, (size_t)nnz * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  EKB_CUDA(cudaMemcpyAsync(d_v, host_v, (size_t)nnz * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  EKB_TRY(coo_scatter(ctx, dev_A, lda, n, nnz, d_ij, d_v));
+  EKB_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx_free(ctx, d_ij);
+  ctx_free(ctx, d_v);
+  return 0;
+}
+
+int ekb200_fill_synthetic(ekb200_ctx* h, int64_t n, uint64_t seed, double offdiag_div, int diag_mode,
+                          double diag_value, double* dev_A, int64_t lda) {
+  CHECK_CTX(h);
+  if (n < 0) return -2;
+  if (lda < n) return -8;
+  return fill_synthetic(ctx, dev_A, lda, n, seed, offdiag_div, diag_mode, diag_value);
+}
+
+int ekb200_dgemm(ekb200_ctx* h, char transa, char transb, int64_t m, int64_t n, int64_t k, double alpha,
+                 const double* A, int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc) {
+  CHECK_CTX(h);
+  int flags = 0;
+  if (transa == 'T' || transa == 't') flags |= GEMM_TA;
+  else if (!(transa == 'N' || transa == 'n')) return -2;
+  if (transb == 'T' || transb == 't') flags |= GEMM_TB;
+  else if (!(transb == 'N' || transb == 'n')) return -3;
+  if (m < 0) return -4;
+  if (n < 0) return -5;
+  if (k < 0) return -6;
+  GemmP p;
+  p.m = (int)m; p.n = (int)n; p.k = (int)k;
+  p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.C = C; p.ldc = ldc;
+  p.alpha = alpha; p.beta = beta;
+  return gemm(ctx, flags, p);
+}
+
+int ekb200_potrf(ekb200_ctx* h, int64_t n, double* B, int64_t ldb) {
+  CHECK_CTX(h);
+  if (n < 0) return -2;
+  if (ldb < n) return -4;
+  if (n == 0) return 0;
+  EKB_TRY(ensure_invd(h, n));
+  return potrf_lower(ctx, n, B, ldb, h->invd);
+}
+
+int ekb200_sygst(ekb200_ctx* h, int64_t n, double* A, int64_t lda, const double* L, int64_t ldl) {
+  CHECK_CTX(h);
+  if (n < 0) return -2;
+  if (lda < n) return -4;
+  if (ldl < n) return -6;
+  if (n == 0) return 0;
+  EKB_TRY(ensure_invd(h, n));
+  EKB_TRY(trtri_diag_blocks(ctx, n, L, ldl, h->invd));
+  EKB_TRY(sygst_lower(ctx, n, A, lda, L, ldl, h->invd));
+  EKB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int ekb200_trtrs_lt(ekb200_ctx* h, int64_t n, int64_t nrhs, const double* L, int64_t ldl, double* Z, int64_t ldz) {
+  CHECK_CTX(h);
+  if (n < 0) return -2;
+  if (nrhs < 0) return -3;
+  if (ldl < n) return -5;
+  if (ldz < n) return -7;
+  if (n == 0 || nrhs == 0) return 0;
+  EKB_TRY(ensure_invd(h, n));
+  EKB_TRY(trtri_diag_blocks(ctx, n, L, ldl, h->invd));
+  EKB_TRY(trsm_lower(ctx, TRSM_LLT, n, nrhs, L, ldl, h->invd, Z, ldz));
+  EKB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int ekb200_measure_fp64_peak(ekb200_ctx* h, double* dmma_tflops, double* dfma_tflops) {
+  CHECK_CTX(h);
+  if (!dmma_tflops) return -2;
+  if (!dfma_tflops) return -3;
+  return measure_fp64_peak(ctx, dmma_tflops, dfma_tflops);
+}
+
+}  // extern "C"

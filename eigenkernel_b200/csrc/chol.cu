@@ -1,0 +1,235 @@
+// Generalized <-> standard conversion: blocked Cholesky (PDPOTRF), reduction to standard form (PDSYGST)
+// and the triangular back-substitution (PDTRTRS).  Reference call sites:
+//   src/generalized_to_standard.f90:24   pdpotrf('L', dim, B, ...)            -> potrf_lower
+//   src/generalized_to_standard.f90:37   pdsygst(1, 'L', dim, A, ..., B, ...) -> sygst_lower
+//   src/generalized_to_standard.f90:103  pdtrtrs('L','T','N', dim, n_vec, B, ..., V, ...) -> trsm_lower(TRSM_LLT)
+//
+// B200 design: everything except 64x64 diagonal-block work is a GEMM on the DMMA engine.  The
+// factorization and the triangular solves recurse by halves (multiples of 64) so the trailing updates
+// are large GEMMs; diagonal blocks are factored and INVERTED in shared memory by one CTA, and a
+// diagonal-block solve is a GEMM with the inverted block.
+#include "common.cuh"
+
+namespace ekb {
+
+constexpr int NB = 64;  // diagonal block size of the triangular machinery
+constexpr size_t LEAF_SMEM = 2 * NB * (NB + 1) * sizeof(double);
+
+// One CTA factors an nb x nb (nb <= 64) diagonal block in shared memory, writes L back (lower part)
+// and its inverse (lower triangular, zero padded to 64x64) to inv.  On a non-positive pivot the first
+// failing global index (1-based) is recorded with atomicMin in *info (0 = none yet is stored as INT_MAX).
+__global__ void __launch_bounds__(256) potrf_leaf_kernel(double* __restrict__ A, i64 lda, int nb, double* __restrict__ inv,
+                                                         int* __restrict__ info, int global_offset) {
+  extern __shared__ double dsm[];
+  double(*s)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(dsm);
+  double(*si)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(dsm + NB * (NB + 1));
+  const int tid = threadIdx.x;
+  for (int e = tid; e < NB * NB; e += blockDim.x) {
+    int r = e % NB, c = e / NB;
+    s[r][c] = (r < nb && c < nb && r >= c) ? A[(i64)c * lda + r] : (r == c ? 1.0 : 0.0);
+  }
+  __syncthreads();
+  for (int j = 0; j < nb; ++j) {
+    double d = s[j][j];
+    __syncthreads();
+    if (!(d > 0.0)) {
+      if (tid == 0) atomicMin(info, global_offset + j + 1);
+      d = 1.0;
+    }
+    double sd = sqrt(d);
+    if (tid < NB) {
+      if (tid == j) s[j][j] = sd;
+      else if (tid > j) s[tid][j] /= sd;
+    }
+    __syncthreads();
+    // trailing update of the lower triangle: s[r][c] -= s[r][j] * s[c][j], r >= c > j
+    const int rem = nb - j - 1;
+    for (int e = tid; e < rem * rem; e += blockDim.x) {
+      int r = j + 1 + e % rem, c = j + 1 + e / rem;
+      if (r >= c) s[r][c] -= s[r][j] * s[c][j];
+    }
+    __syncthreads();
+  }
+  // inverse by forward substitution, one column per thread
+  if (tid < NB) {
+    const int c = tid;
+    for (int i = 0; i < NB; ++i) si[i][c] = 0.0;
+    if (c < nb) {
+      for (int i = c; i < nb; ++i) {
+        double acc = (i == c) ? 1.0 : 0.0;
+        for (int k = c; k < i; ++k) acc -= s[i][k] * si[k][c];
+        si[i][c] = acc / s[i][i];
+      }
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < NB * NB; e += blockDim.x) {
+    int r = e % NB, c = e / NB;
+    if (r < nb && c < nb && r >= c) A[(i64)c * lda + r] = s[r][c];
+    inv[e] = si[r][c];
+  }
+}
+
+// Invert every 64x64 diagonal block of a given lower-triangular L (used when L did not come from potrf_lower).
+__global__ void __launch_bounds__(64) trtri_blocks_kernel(const double* __restrict__ L, i64 ldl, i64 n,
+                                                          double* __restrict__ invd) {
+  extern __shared__ double dsm[];
+  double(*s)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(dsm);
+  double(*si)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(dsm + NB * (NB + 1));
+  const int blk = blockIdx.x, tid = threadIdx.x;
+  const i64 o = (i64)blk * NB;
+  const int nb = (int)((n - o) < NB ? (n - o) : NB);
+  for (int e = tid; e < NB * NB; e += blockDim.x) {
+    int r = e % NB, c = e / NB;
+    s[r][c] = (r < nb && c < nb && r >= c) ? L[(o + c) * ldl + o + r] : (r == c ? 1.0 : 0.0);
+  }
+  __syncthreads();
+  const int c = tid;
+  for (int i = 0; i < NB; ++i) si[i][c] = 0.0;
+  if (c < nb) {
+    for (int i = c; i < nb; ++i) {
+      double acc = (i == c) ? 1.0 : 0.0;
+      for (int k = c; k < i; ++k) acc -= s[i][k] * si[k][c];
+      si[i][c] = acc / s[i][i];
+    }
+  }
+  __syncthreads();
+  double* inv = invd + (i64)blk * NB * NB;
+  for (int e = tid; e < NB * NB; e += blockDim.x) inv[e] = si[e % NB][e / NB];
+}
+
+int trtri_diag_blocks(Ctx* ctx, i64 n, const double* L, i64 ldl, double* invd) {
+  if (n <= 0) return 0;
+  static bool attr = false;
+  if (!attr) {
+    EKB_CUDA(cudaFuncSetAttribute(trtri_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LEAF_SMEM));
+    attr = true;
+  }
+  trtri_blocks_kernel<<<cdiv(n, NB), 64, LEAF_SMEM, ctx->stream>>>(L, ldl, n, invd);
+  EKB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------- recursive triangular solve
+// tmp: workspace of at least max(m,n) * 64 doubles.
+static int trsm_rec(Ctx* ctx, int kind, i64 m, i64 n, const double* L, i64 ldl, const double* invd, double* B,
+                    i64 ldb, double* tmp) {
+  const i64 ln = (kind == TRSM_RLT) ? n : m;  // order of L
+  if (ln <= 0 || m <= 0 || n <= 0) return 0;
+  if (ln <= NB) {
+    GemmP p;
+    p.alpha = 1.0;
+    p.beta = 0.0;
+    if (kind == TRSM_RLT) {  // X = B * inv^T  (m x ln)
+      p.m = (int)m; p.n = (int)ln; p.k = (int)ln;
+      p.A = B; p.lda = ldb; p.B = invd; p.ldb = NB; p.C = tmp; p.ldc = m;
+      EKB_TRY(gemm(ctx, GEMM_TB, p));
+      EKB_TRY(copy_matrix(ctx, tmp, m, B, ldb, m, ln));
+    } else {  // X = inv * B or inv^T * B   (ln x n)
+      p.m = (int)ln; p.n = (int)n; p.k = (int)ln;
+      p.A = invd; p.lda = NB; p.B = B; p.ldb = ldb; p.C = tmp; p.ldc = NB;
+      EKB_TRY(gemm(ctx, kind == TRSM_LLT ? GEMM_TA : 0, p));
+      EKB_TRY(copy_matrix(ctx, tmp, NB, B, ldb, ln, n));
+    }
+    return 0;
+  }
+  const i64 nblk = (ln + NB - 1) / NB;
+  const i64 n1 = ((nblk + 1) / 2) * NB, n2 = ln - n1;
+  const double* L11 = L;
+  const double* L21 = L + n1;
+  const double* L22 = L + n1 * ldl + n1;
+  const double* inv2 = invd + (n1 / NB) * NB * NB;
+  GemmP p;
+  p.alpha = -1.0;
+  p.beta = 1.0;
+  if (kind == TRSM_RLT) {
+    double* B1 = B;
+    double* B2 = B + n1 * ldb;
+    EKB_TRY(trsm_rec(ctx, kind, m, n1, L11, ldl, invd, B1, ldb, tmp));
+    p.m = (int)m; p.n = (int)n2; p.k = (int)n1;  // B2 -= X1 * L21^T
+    p.A = B1; p.lda = ldb; p.B = L21; p.ldb = ldl; p.C = B2; p.ldc = ldb;
+    EKB_TRY(gemm(ctx, GEMM_TB, p));
+    EKB_TRY(trsm_rec(ctx, kind, m, n2, L22, ldl, inv2, B2, ldb, tmp));
+  } else if (kind == TRSM_LLN) {
+    double* B1 = B;
+    double* B2 = B + n1;
+    EKB_TRY(trsm_rec(ctx, kind, n1, n, L11, ldl, invd, B1, ldb, tmp));
+    p.m = (int)n2; p.n = (int)n; p.k = (int)n1;  // B2 -= L21 * X1
+    p.A = L21; p.lda = ldl; p.B = B1; p.ldb = ldb; p.C = B2; p.ldc = ldb;
+    EKB_TRY(gemm(ctx, 0, p));
+    EKB_TRY(trsm_rec(ctx, kind, n2, n, L22, ldl, inv2, B2, ldb, tmp));
+  } else {  // TRSM_LLT
+    double* B1 = B;
+    double* B2 = B + n1;
+    EKB_TRY(trsm_rec(ctx, kind, n2, n, L22, ldl, inv2, B2, ldb, tmp));
+    p.m = (int)n1; p.n = (int)n; p.k = (int)n2;  // B1 -= L21^T * X2
+    p.A = L21; p.lda = ldl; p.B = B2; p.ldb = ldb; p.C = B1; p.ldc = ldb;
+    EKB_TRY(gemm(ctx, GEMM_TA, p));
+    EKB_TRY(trsm_rec(ctx, kind, n1, n, L11, ldl, invd, B1, ldb, tmp));
+  }
+  return 0;
+}
+
+int trsm_lower(Ctx* ctx, int kind, i64 m, i64 n, const double* L, i64 ldl, const double* invd, double* Bm, i64 ldb) {
+  if (m <= 0 || n <= 0) return 0;
+  double* tmp = nullptr;
+  i64 mx = m > n ? m : n;
+  EKB_TRY(ctx_alloc(ctx, (void**)&tmp, (size_t)round_up(mx, 2) * NB * sizeof(double)));
+  int rc = trsm_rec(ctx, kind, m, n, L, ldl, invd, Bm, ldb, tmp);
+  cudaStreamSynchronize(ctx->stream);
+  ctx_free(ctx, tmp);
+  return rc;
+}
+
+// ---------------------------------------------------------------- recursive Cholesky
+static int potrf_rec(Ctx* ctx, i64 n, double* A, i64 lda, double* invd, i64 goff, double* tmp) {
+  if (n <= 0) return 0;
+  if (n <= NB) {
+    static bool attr = false;
+    if (!attr) {
+      EKB_CUDA(cudaFuncSetAttribute(potrf_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LEAF_SMEM));
+      attr = true;
+    }
+    potrf_leaf_kernel<<<1, 256, LEAF_SMEM, ctx->stream>>>(A, lda, (int)n, invd, ctx->d_info, (int)goff);
+    EKB_CUDA(cudaGetLastError());
+    return 0;
+  }
+  const i64 nblk = (n + NB - 1) / NB;
+  const i64 n1 = ((nblk + 1) / 2) * NB, n2 = n - n1;
+  double* A21 = A + n1;
+  double* A22 = A + n1 * lda + n1;
+  EKB_TRY(potrf_rec(ctx, n1, A, lda, invd, goff, tmp));
+  EKB_TRY(trsm_rec(ctx, TRSM_RLT, n2, n1, A, lda, invd, A21, lda, tmp));
+  GemmP p;
+  p.m = (int)n2; p.n = (int)n2; p.k = (int)n1;
+  p.A = A21; p.lda = lda; p.B = A21; p.ldb = lda; p.C = A22; p.ldc = lda;
+  p.alpha = -1.0; p.beta = 1.0;
+  EKB_TRY(gemm(ctx, GEMM_TB, p, /*tri_keep=*/1));
+  return potrf_rec(ctx, n2, A22, lda, invd + (n1 / NB) * NB * NB, goff + n1, tmp);
+}
+
+int potrf_lower(Ctx* ctx, i64 n, double* B, i64 ldb, double* invd) {
+  if (n <= 0) return 0;
+  double* tmp = nullptr;
+  EKB_TRY(ctx_alloc(ctx, (void**)&tmp, (size_t)round_up(n, 2) * NB * sizeof(double)));
+  *ctx->h_info = 0x7fffffff;
+  EKB_CUDA(cudaMemcpyAsync(ctx->d_info, ctx->h_info, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  int rc = potrf_rec(ctx, n, B, ldb, invd, 0, tmp);
+  if (rc == 0) {
+    EKB_CUDA(cudaMemcpyAsync(ctx->h_info, ctx->d_info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    EKB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (*ctx->h_info != 0x7fffffff) rc = *ctx->h_info;
+  }
+  ctx_free(ctx, tmp);
+  return rc;
+}
+
+// A <- L^-1 A L^-T as two full triangular solves (2 n^3 FLOPs, all on the GEMM engine).
+// Requires the full symmetric A on entry; both triangles hold the result on exit.
+int sygst_lower(Ctx* ctx, i64 n, double* A, i64 lda, const double* L, i64 ldl, const double* invd) {
+  EKB_TRY(trsm_lower(ctx, TRSM_LLN, n, n, L, ldl, invd, A, lda));
+  EKB_TRY(trsm_lower(ctx, TRSM_RLT, n, n, L, ldl, invd, A, lda));
+  return 0;
+}
+
+}  // namespace ekb

@@ -1,0 +1,114 @@
+// Shared declarations of libekb200: context, error convention, stage timers, kernel launch helpers.
+// B200-native (sm_100a) dense FP64 symmetric eigensolver behind EigenKernel's solver boundary
+// (reference: src/solver_main.f90:52-99).  No cuSOLVER / cuBLAS / CPU fallback on the solve path.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+namespace ekb {
+
+typedef long long i64;
+
+// LAPACK-style info codes of the C-ABI: 0 ok, <0 argument -i illegal, >0 numerical failure.
+// Internal CUDA failures map to EKB_ERR_CUDA.
+enum { EKB_ERR_CUDA = 1000001, EKB_ERR_NOMEM = 1000002, EKB_ERR_INTERNAL = 1000003 };
+
+struct Event {
+  std::string name;
+  double seconds;
+  int num_repeated;
+};
+
+// Device-memory arena: one cudaMalloc'd slab per request, freed with the context.
+struct Ctx {
+  int device = 0;
+  int num_sms = 148;
+  cudaStream_t stream = nullptr;
+  std::vector<Event> events;          // timing table replayed through add_event by the caller
+  std::vector<void*> allocs;          // every device allocation owned by the context
+  cudaError_t last_cuda = cudaSuccess;
+  // scratch
+  double* splitk_ws = nullptr;        // split-K partial sums
+  size_t splitk_ws_bytes = 0;
+  int* d_info = nullptr;              // device-side info word(s)
+  int* h_info = nullptr;              // pinned mirror
+  // options
+  int band = 64;                      // b: half bandwidth of the two-stage reduction
+  // stage timers
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string last_error;
+};
+
+#define EKB_CUDA(call)                                                                      \
+  do {                                                                                      \
+    cudaError_t _e = (call);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      ctx->last_cuda = _e;                                                                  \
+      ctx->last_error = std::string(#call) + ": " + cudaGetErrorString(_e);                 \
+      return EKB_ERR_CUDA;                                                                  \
+    }                                                                                       \
+  } while (0)
+
+#define EKB_TRY(call)             \
+  do {                            \
+    int _i = (call);              \
+    if (_i != 0) return _i;       \
+  } while (0)
+
+int ctx_alloc(Ctx* ctx, void** p, size_t bytes);
+int ctx_free(Ctx* ctx, void* p);
+void ctx_add_event(Ctx* ctx, const char* name, double seconds);
+
+// Scoped stage timer on the context stream (CUDA events, device time).
+struct StageTimer {
+  Ctx* ctx;
+  const char* name;
+  cudaEvent_t a, b;
+  StageTimer(Ctx* c, const char* n);
+  double stop();  // records, synchronises, adds the event; returns seconds
+};
+
+static inline int cdiv(i64 a, i64 b) { return (int)((a + b - 1) / b); }
+static inline i64 round_up(i64 a, i64 b) { return (a + b - 1) / b * b; }
+
+// ---------------------------------------------------------------- GEMM engine (gemm.cu)
+// C(m x n) = alpha * op(A)(m x k) * op(B)(k x n) + beta * C, column-major, FP64 on DMMA.8x8x4 tiles.
+struct GemmP {
+  int m, n, k;
+  const double* A;
+  const double* B;
+  double* C;
+  i64 lda, ldb, ldc;
+  double alpha, beta;
+};
+enum GemmFlags {
+  GEMM_TA = 1,      // op(A) = A^T
+  GEMM_TB = 2,      // op(B) = B^T
+  GEMM_SYMA = 4,    // A is symmetric, only elements with (col - row) < 128 are valid (NN only)
+};
+// tri_keep < 0: full C.  Otherwise only elements with (col - row) < tri_keep are guaranteed to be
+// computed (whole tiles above that region are skipped): 1 = lower triangle, 128 = lower + a 128 band.
+int gemm(Ctx* ctx, int flags, const GemmP& p, int tri_keep = -1, int splitk = 1);
+// Batched: `batch` is a DEVICE array of nb problems; (max_m, max_n) bound the grid.
+int gemm_batched(Ctx* ctx, int flags, const GemmP* d_batch, int nb, int max_m, int max_n);
+
+// ---------------------------------------------------------------- elementwise helpers (fill.cu)
+int fill_synthetic(Ctx* ctx, double* A, i64 lda, i64 n, uint64_t seed, double offdiag_scale, int diag_mode,
+                   double diag_value);
+int set_zero(Ctx* ctx, double* A, i64 lda, i64 m, i64 n);
+int copy_matrix(Ctx* ctx, const double* A, i64 lda, double* B, i64 ldb, i64 m, i64 n);
+int set_identity(Ctx* ctx, double* A, i64 lda, i64 n);
+int coo_scatter(Ctx* ctx, double* A, i64 lda, i64 n, i64 nnz, const int32_t* d_ij, const double* d_v);
+int symmetrize_from_lower(Ctx* ctx, double* A, i64 lda, i64 n);
+
+// ---------------------------------------------------------------- stages
+int potrf_lower(Ctx* ctx, i64 n, double* B, i64 ldb, double* invd /* n x 64 inverted diagonal blocks */);
+enum TrsmKind { TRSM_RLT = 0 /* X L^T = B */, TRSM_LLN = 1 /* L X = B */, TRSM_LLT = 2 /* L^T X = B */ };
+int trsm_lower(Ctx* ctx, int kind, i64 m, i64 n, const double* L, i64 ldl, const double* invd, double* Bm, i64 ldb);
+int trtri_diag_blocks(Ctx* ctx, i64 n, const double* L, i64 ldl, double* invd);
+int sygst_lower(Ctx* ctx, i64 n, double* A, i64 lda, const double* L, i64 ldl, const double* invd);
+
+}  // namespace ekb

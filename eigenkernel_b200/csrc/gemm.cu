@@ -1,0 +1,290 @@
+// FP64 GEMM engine on DMMA.8x8x4 tensor-core tiles (sm_100a).
+//
+// Every GEMM-shaped step of the eigensolve (PDPOTRF/PDSYGST/PDTRTRS trailing updates, the SYMM and
+// SYR2K of the dense->band reduction, the D&C merge products and both back-transformations; reference
+// call sites generalized_to_standard.f90:24,37,103 and solver_scalapack_all.f90:59,96,115) runs through
+// this one kernel family.  tcgen05/UMMA has no f64 kind, so the Blackwell FP64 tensor path is
+// mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4) fed from shared memory that is filled by a 4-stage cp.async
+// (LDGSTS) pipeline.
+//
+// Layout trick: the MMA is issued on the TRANSPOSED problem (MMA "row" operand = op(B)^T, "col"
+// operand = op(A)^T) so that the two accumulators a thread owns are adjacent in the column-major M
+// direction -> 16-byte vector stores to C.
+//
+// Shared-memory layouts (doubles), both bank-conflict free for the fragment pattern
+// (mn = base + lane/4, k = k4 + lane%4):
+//   K-major  (operand contiguous in k in global):  s[mn * (BK+4) + k]
+//   MN-major (operand contiguous in m/n in global): s[k * (BMN+4) + mn]
+#include "common.cuh"
+
+namespace ekb {
+
+constexpr int BK = 16;
+constexpr int LDK = BK + 4;  // K-major row stride
+constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_STAGES = 4;
+
+__device__ __forceinline__ void cp_async16(double* smem, const double* g, int bytes) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(g), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async8(double* smem, const double* g, int bytes) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(g), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+// Load one (BMN x BK) operand tile.  Element (mn, k) lives at g[(mn0+mn) * s_mn + (k0+k) * s_k] where
+// exactly one of the two global strides is 1 (kmajor: s_k == 1).
+template <int BMN>
+__device__ __forceinline__ void load_tile(double* s, const double* __restrict__ g, i64 ld, bool kmajor, bool al16,
+                                          int mn0, int k0, int mn_lim, int k_lim, int tid) {
+  if (kmajor) {
+    if (al16) {
+#pragma unroll
+      for (int c = tid; c < BMN * (BK / 2); c += GEMM_THREADS) {
+        int mn = c / (BK / 2), kc = (c % (BK / 2)) * 2;
+        int gm = mn0 + mn, gk = k0 + kc;
+        int bytes = (gm < mn_lim) ? max(0, min(16, (k_lim - gk) * 8)) : 0;
+        const double* src = bytes > 0 ? g + (i64)gm * ld + gk : g;
+        cp_async16(s + mn * LDK + kc, src, bytes);
+      }
+    } else {
+#pragma unroll
+      for (int c = tid; c < BMN * BK; c += GEMM_THREADS) {
+        int mn = c / BK, kc = c % BK;
+        int gm = mn0 + mn, gk = k0 + kc;
+        int bytes = (gm < mn_lim && gk < k_lim) ? 8 : 0;
+        const double* src = bytes > 0 ? g + (i64)gm * ld + gk : g;
+        cp_async8(s + mn * LDK + kc, src, bytes);
+      }
+    }
+  } else {
+    constexpr int LDM = BMN + 4;
+    if (al16) {
+#pragma unroll
+      for (int c = tid; c < BK * (BMN / 2); c += GEMM_THREADS) {
+        int k = c / (BMN / 2), mc = (c % (BMN / 2)) * 2;
+        int gm = mn0 + mc, gk = k0 + k;
+        int bytes = (gk < k_lim) ? max(0, min(16, (mn_lim - gm) * 8)) : 0;
+        const double* src = bytes > 0 ? g + (i64)gk * ld + gm : g;
+        cp_async16(s + k * LDM + mc, src, bytes);
+      }
+    } else {
+#pragma unroll
+      for (int c = tid; c < BK * BMN; c += GEMM_THREADS) {
+        int k = c / BMN, mc = c % BMN;
+        int gm = mn0 + mc, gk = k0 + k;
+        int bytes = (gk < k_lim && gm < mn_lim) ? 8 : 0;
+        const double* src = bytes > 0 ? g + (i64)gk * ld + gm : g;
+        cp_async8(s + k * LDM + mc, src, bytes);
+      }
+    }
+  }
+}
+
+template <int BM, int BN, int WM, int WN, bool BATCHED>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_kernel(GemmP p0, const GemmP* __restrict__ batch, int flags, int tri_keep, int splitk, double* __restrict__ ws) {
+  extern __shared__ __align__(16) double smem[];
+  constexpr int A_TILE = BM * LDK;  // >= BK*(BM+4)
+  constexpr int B_TILE = BN * LDK;
+  constexpr int MI = WM / 8, NI = WN / 8;
+  constexpr int WARPS_M = BM / WM;
+  static_assert((BM / WM) * (BN / WN) == GEMM_THREADS / 32, "8 warps");
+
+  GemmP p = p0;
+  if (BATCHED) p = batch[blockIdx.z];
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  if (m0 >= p.m || n0 >= p.n) return;
+  if (tri_keep >= 0 && n0 - (m0 + BM - 1) >= tri_keep) return;
+
+  int kt_begin = 0, kt_end = (p.k + BK - 1) / BK;
+  double alpha = p.alpha, beta = p.beta;
+  double* C = p.C;
+  i64 ldc = p.ldc;
+  if (!BATCHED && splitk > 1) {
+    int per = (kt_end + splitk - 1) / splitk;
+    kt_begin = blockIdx.z * per;
+    kt_end = min(kt_end, kt_begin + per);
+    C = ws + (i64)blockIdx.z * p.m * p.n;
+    ldc = p.m;
+    alpha = 1.0;
+    beta = 0.0;
+  }
+  const int nk = max(0, kt_end - kt_begin);
+
+  const bool ta = flags & GEMM_TA, tb = flags & GEMM_TB, syma = flags & GEMM_SYMA;
+  const bool al16 = ((((uintptr_t)p.A | (uintptr_t)p.B) & 15) == 0) && ((p.lda | p.ldb) & 1) == 0;
+  const bool b_kmajor = !tb;
+
+  double* sA = smem;
+  double* sB = smem + GEMM_STAGES * A_TILE;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp % WARPS_M, wn = warp / WARPS_M;
+  const int lq = lane >> 2, lr = lane & 3;
+
+  auto a_is_kmajor = [&](int kt) -> bool {
+    if (syma) return (kt * BK) >= m0 + BM;
+    return ta;
+  };
+  auto issue = [&](int kt, int stage) {
+    const int k0 = kt * BK;
+    load_tile<BM>(sA + stage * A_TILE, p.A, p.lda, a_is_kmajor(kt), al16, m0, k0, p.m, p.k, tid);
+    load_tile<BN>(sB + stage * B_TILE, p.B, p.ldb, b_kmajor, al16, n0, k0, p.n, p.k, tid);
+  };
+
+  double acc[MI][NI][2];
+#pragma unroll
+  for (int i = 0; i < MI; ++i)
+#pragma unroll
+    for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+#pragma unroll
+  for (int s = 0; s < GEMM_STAGES - 1; ++s) {
+    if (s < nk) issue(kt_begin + s, s);
+    cp_async_commit();
+  }
+
+  const int b_smn = b_kmajor ? LDK : 1, b_sk = b_kmajor ? 1 : (BN + 4);
+  const int b_off = (wn * WN + lq) * b_smn + lr * b_sk;
+
+  for (int it = 0; it < nk; ++it) {
+    cp_async_wait<GEMM_STAGES - 2>();
+    __syncthreads();
+    {
+      int nx = it + GEMM_STAGES - 1;
+      if (nx < nk) issue(kt_begin + nx, nx % GEMM_STAGES);
+      cp_async_commit();
+    }
+    const int stage = it % GEMM_STAGES;
+    const bool akm = a_is_kmajor(kt_begin + it);
+    const int a_smn = akm ? LDK : 1, a_sk = akm ? 1 : (BM + 4);
+    const double* tA = sA + stage * A_TILE + (wm * WM + lq) * a_smn + lr * a_sk;
+    const double* tB = sB + stage * B_TILE + b_off;
+#pragma unroll
+    for (int kk = 0; kk < BK / 4; ++kk) {
+      double af[MI], bf[NI];
+#pragma unroll
+      for (int i = 0; i < MI; ++i) af[i] = tA[i * 8 * a_smn + kk * 4 * a_sk];
+#pragma unroll
+      for (int j = 0; j < NI; ++j) bf[j] = tB[j * 8 * b_smn + kk * 4 * b_sk];
+#pragma unroll
+      for (int i = 0; i < MI; ++i)
+#pragma unroll
+        for (int j = 0; j < NI; ++j) dmma884(acc[i][j][0], acc[i][j][1], bf[j], af[i]);
+    }
+  }
+  cp_async_wait<0>();
+
+  // epilogue: thread owns C(m0w + i*8 + 2*lr + {0,1}, n0w + j*8 + lq)
+  const bool cvec = (((uintptr_t)C & 15) == 0) && ((ldc & 1) == 0);
+#pragma unroll
+  for (int j = 0; j < NI; ++j) {
+    const int col = n0 + wn * WN + j * 8 + lq;
+    if (col >= p.n) continue;
+#pragma unroll
+    for (int i = 0; i < MI; ++i) {
+      const int row = m0 + wm * WM + i * 8 + 2 * lr;
+      if (row >= p.m) continue;
+      double* cp = C + (i64)col * ldc + row;
+      double v0 = alpha * acc[i][j][0], v1 = alpha * acc[i][j][1];
+      if (row + 1 < p.m && cvec) {
+        if (beta != 0.0) {
+          double2 old = *reinterpret_cast<const double2*>(cp);
+          v0 += beta * old.x;
+          v1 += beta * old.y;
+        }
+        *reinterpret_cast<double2*>(cp) = make_double2(v0, v1);
+      } else {
+        if (beta != 0.0) v0 += beta * cp[0];
+        cp[0] = v0;
+        if (row + 1 < p.m) {
+          if (beta != 0.0) v1 += beta * cp[1];
+          cp[1] = v1;
+        }
+      }
+    }
+  }
+}
+
+__global__ void splitk_reduce_kernel(const double* __restrict__ ws, int splitk, int m, int n, double* __restrict__ C,
+                                     i64 ldc, double alpha, double beta, int tri_keep) {
+  i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  i64 tot = (i64)m * n;
+  if (idx >= tot) return;
+  int r = (int)(idx % m), c = (int)(idx / m);
+  double s = 0.0;
+  for (int z = 0; z < splitk; ++z) s += ws[(i64)z * tot + idx];
+  double* cp = C + (i64)c * ldc + r;
+  double v = alpha * s;
+  if (beta != 0.0) v += beta * *cp;
+  *cp = v;
+}
+
+template <int BM, int BN, int WM, int WN, bool BATCHED>
+static int launch_cfg(Ctx* ctx, int flags, const GemmP& p, const GemmP* d_batch, int nb, int max_m, int max_n,
+                      int tri_keep, int splitk) {
+  constexpr size_t smem = (size_t)GEMM_STAGES * (BM + BN) * LDK * sizeof(double);
+  static bool attr_set = false;
+  auto kern = gemm_kernel<BM, BN, WM, WN, BATCHED>;
+  if (!attr_set) {
+    EKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  dim3 grid(cdiv(max_m, BM), cdiv(max_n, BN), BATCHED ? nb : splitk);
+  kern<<<grid, GEMM_THREADS, smem, ctx->stream>>>(p, d_batch, flags, tri_keep, splitk, ctx->splitk_ws);
+  EKB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int gemm(Ctx* ctx, int flags, const GemmP& p, int tri_keep, int splitk) {
+  if (p.m <= 0 || p.n <= 0) return 0;
+  if (splitk > 1) {
+    int nkt = cdiv(p.k, BK);
+    if (splitk > nkt) splitk = nkt > 0 ? nkt : 1;
+    size_t need = (size_t)splitk * p.m * p.n * sizeof(double);
+    if (need > ctx->splitk_ws_bytes) {
+      if (ctx->splitk_ws) ctx_free(ctx, ctx->splitk_ws);
+      ctx->splitk_ws = nullptr;
+      ctx->splitk_ws_bytes = 0;
+      size_t want = need < ((size_t)64 << 20) ? ((size_t)64 << 20) : need;
+      EKB_TRY(ctx_alloc(ctx, (void**)&ctx->splitk_ws, want));
+      ctx->splitk_ws_bytes = want;
+    }
+  }
+  if (splitk < 1) splitk = 1;
+  int rc;
+  if (p.n <= 64)
+    rc = launch_cfg<128, 64, 32, 32, false>(ctx, flags, p, nullptr, 1, p.m, p.n, tri_keep, splitk);
+  else if (p.m <= 64)
+    rc = launch_cfg<64, 128, 32, 32, false>(ctx, flags, p, nullptr, 1, p.m, p.n, tri_keep, splitk);
+  else
+    rc = launch_cfg<128, 128, 64, 32, false>(ctx, flags, p, nullptr, 1, p.m, p.n, tri_keep, splitk);
+  if (rc) return rc;
+  if (splitk > 1) {
+    i64 tot = (i64)p.m * p.n;
+    splitk_reduce_kernel<<<cdiv(tot, 256), 256, 0, ctx->stream>>>(ctx->splitk_ws, splitk, p.m, p.n, p.C, p.ldc,
+                                                                 p.alpha, p.beta, tri_keep);
+    EKB_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+int gemm_batched(Ctx* ctx, int flags, const GemmP* d_batch, int nb, int max_m, int max_n) {
+  if (nb <= 0 || max_m <= 0 || max_n <= 0) return 0;
+  GemmP dummy = {};
+  if (max_n <= 64) return launch_cfg<128, 64, 32, 32, true>(ctx, flags, dummy, d_batch, nb, max_m, max_n, -1, 1);
+  return launch_cfg<128, 128, 64, 32, true>(ctx, flags, dummy, d_batch, nb, max_m, max_n, -1, 1);
+}
+
+}  // namespace ekb

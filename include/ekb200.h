@@ -1,0 +1,83 @@
+/* libekb200 -- B200-native (sm_100a) dense FP64 symmetric eigensolver: flat C-ABI.
+ *
+ * Drop-in boundary: EigenKernel's solver dispatch `eigen_solver` (reference src/solver_main.f90:22-100).
+ * The new solver names b200 / b200_select / general_b200 / general_b200_select are served by module
+ * ek_solver_b200_m (fortran/solver_b200.f90) which binds the entry points below with ISO_C_BINDING.
+ * Each entry point cites the reference interface it replaces.
+ *
+ * Conventions
+ *  - every function returns a LAPACK-style `info`: 0 = ok, -i = i-th argument illegal, >0 = numerical
+ *    failure (e.g. order of the non-positive leading minor in the Cholesky factorization);
+ *    >= 1000001 = CUDA/internal failure (ekb200_strerror / ekb200_last_error give the text).
+ *    The library never aborts and never prints; the Fortran wrapper turns info != 0 into
+ *    `terminate(msg, info)` exactly as generalized_to_standard.f90:25-30 does.
+ *  - matrices are column-major FP64; `ld*` are leading dimensions in elements; indices are int64.
+ *  - "host" pointers may be pageable; "dev" pointers are device memory of the context's GPU.
+ *  - a context is not thread-safe; different contexts are independent.
+ */
+#ifndef EKB200_H
+#define EKB200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ekb200_ctx ekb200_ctx;
+
+/* ---- context (replaces setup_distribution, src/processes.f90:17-36: one context = one GPU "grid") */
+int ekb200_create(ekb200_ctx** ctx, int device);
+int ekb200_destroy(ekb200_ctx* ctx);
+const char* ekb200_strerror(int info);
+const char* ekb200_last_error(const ekb200_ctx* ctx);
+int ekb200_set_option(ekb200_ctx* ctx, const char* key, int64_t value); /* "band" = half bandwidth b */
+int ekb200_version(void);
+
+/* ---- timing table (replaces add_event, src/event_logger.f90:23-65; seconds are CUDA-event times) */
+int ekb200_num_events(const ekb200_ctx* ctx);
+int ekb200_get_event(const ekb200_ctx* ctx, int i, const char** name, double* seconds, int* num_repeated);
+int ekb200_clear_events(ekb200_ctx* ctx);
+
+/* ---- device memory owned by the context (replaces the allocatable arrays of
+ *      setup_distributed_matrix, src/distribute_matrix.f90:92-148) */
+int ekb200_dev_alloc(ekb200_ctx* ctx, int64_t bytes, void** dev_ptr);
+int ekb200_dev_free(ekb200_ctx* ctx, void* dev_ptr);
+int ekb200_h2d(ekb200_ctx* ctx, void* dev_dst, const void* host_src, int64_t bytes);
+int ekb200_d2h(ekb200_ctx* ctx, void* host_dst, const void* dev_src, int64_t bytes);
+int ekb200_h2d_matrix(ekb200_ctx* ctx, double* dev_dst, int64_t ldd, const double* host_src, int64_t lds, int64_t m,
+                      int64_t n);
+int ekb200_d2h_matrix(ekb200_ctx* ctx, double* host_dst, int64_t ldh, const double* dev_src, int64_t ldd, int64_t m,
+                      int64_t n);
+int ekb200_sync(ekb200_ctx* ctx);
+
+/* ---- input construction on the device
+ * ekb200_coo_to_dense: distribute_global_sparse_matrix (src/distribute_matrix.f90:401-422): zero A, scatter
+ *   the 1-based COO entries `ij` (Fortran suffix(2,nnz)) with symmetric mirroring.  Host COO in.
+ * ekb200_fill_synthetic: counter-hash generator of SURVEY.md 8(d): off-diagonal u(seed,i,j)/offdiag_div,
+ *   diagonal u+diag_value (diag_mode 0) or diag_value (diag_mode 1). */
+int ekb200_coo_to_dense(ekb200_ctx* ctx, int64_t n, int64_t nnz, const int32_t* host_ij, const double* host_v,
+                        double* dev_A, int64_t lda);
+int ekb200_fill_synthetic(ekb200_ctx* ctx, int64_t n, uint64_t seed, double offdiag_div, int diag_mode,
+                          double diag_value, double* dev_A, int64_t lda);
+
+/* ---- stage-level entry points on device-resident matrices (hybrids, per-stage tests, ncu targets).
+ * ekb200_dgemm: the DMMA GEMM engine; transa/transb are 'N' or 'T'.  (PBLAS pdgemm, distribute_matrix.f90:47) */
+int ekb200_dgemm(ekb200_ctx* ctx, char transa, char transb, int64_t m, int64_t n, int64_t k, double alpha,
+                 const double* dev_A, int64_t lda, const double* dev_B, int64_t ldb, double beta, double* dev_C,
+                 int64_t ldc);
+/* ekb200_potrf: pdpotrf('L') (generalized_to_standard.f90:24). B <- L (lower; strict upper left untouched).
+ *   info = i > 0: leading minor of order i not positive definite. */
+int ekb200_potrf(ekb200_ctx* ctx, int64_t n, double* dev_B, int64_t ldb);
+/* ekb200_sygst: pdsygst(1,'L') (generalized_to_standard.f90:37). A <- L^-1 A L^-T.  A must hold the full
+ *   symmetric matrix on entry; on exit both triangles hold the (symmetric) result. L from ekb200_potrf. */
+int ekb200_sygst(ekb200_ctx* ctx, int64_t n, double* dev_A, int64_t lda, const double* dev_L, int64_t ldl);
+/* ekb200_trtrs_lt: pdtrtrs('L','T','N') (generalized_to_standard.f90:103). Z <- L^-T Z, Z is n x nrhs. */
+int ekb200_trtrs_lt(ekb200_ctx* ctx, int64_t n, int64_t nrhs, const double* dev_L, int64_t ldl, double* dev_Z,
+                    int64_t ldz);
+
+/* ---- measurement helper (roofline denominator; never on the solve path) */
+int ekb200_measure_fp64_peak(ekb200_ctx* ctx, double* dmma_tflops, double* dfma_tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EKB200_H */
