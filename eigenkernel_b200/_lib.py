@@ -48,6 +48,9 @@ _SIGS = {
     "ekb200_potrf": [c_void_p, c_int64, c_void_p, c_int64],
     "ekb200_sygst": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64],
     "ekb200_trtrs_lt": [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64],
+    "ekb200_sy2sb": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p],
+    "ekb200_sy2sb_num_panels": [c_void_p, c_int64],
+    "ekb200_get_band": [c_void_p],
     "ekb200_measure_fp64_peak": [c_void_p, POINTER(c_double), POINTER(c_double)],
 }
 _RESTYPE = {"ekb200_strerror": c_char_p, "ekb200_last_error": c_char_p}

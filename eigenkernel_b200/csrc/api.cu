@@ -241,6 +241,24 @@ int ekb200_trtrs_lt(ekb200_ctx* h, int64_t n, int64_t nrhs, const double* L, int
   return 0;
 }
 
+int ekb200_get_band(const ekb200_ctx* h) { return h ? h->c.band : 0; }
+int ekb200_sy2sb_num_panels(const ekb200_ctx* h, int64_t n) { return h ? sy2sb_num_panels(n, h->c.band) : 0; }
+
+int ekb200_sy2sb(ekb200_ctx* h, int64_t n, double* A, int64_t lda, double* AB, int64_t ldab, double* T1) {
+  CHECK_CTX(h);
+  if (n < 0) return -2;
+  if (lda < n) return -4;
+  if (ldab < 2 * ctx->band) return -6;
+  if (n == 0) return 0;
+  double* work = nullptr;
+  EKB_TRY(ctx_alloc(ctx, (void**)&work, sy2sb_workspace_doubles(n, ctx->band, ctx->num_sms) * sizeof(double)));
+  int rc = sy2sb(ctx, n, ctx->band, A, lda, AB, ldab, T1, work);
+  cudaStreamSynchronize(ctx->stream);
+  ctx_free(ctx, work);
+  if (rc == 0) EKB_CUDA(cudaGetLastError());
+  return rc;
+}
+
 int ekb200_measure_fp64_peak(ekb200_ctx* h, double* dmma_tflops, double* dfma_tflops) {
   CHECK_CTX(h);
   if (!dmma_tflops) return -2;

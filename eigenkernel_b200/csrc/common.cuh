@@ -111,4 +111,9 @@ int trsm_lower(Ctx* ctx, int kind, i64 m, i64 n, const double* L, i64 ldl, const
 int trtri_diag_blocks(Ctx* ctx, i64 n, const double* L, i64 ldl, double* invd);
 int sygst_lower(Ctx* ctx, i64 n, double* A, i64 lda, const double* L, i64 ldl, const double* invd);
 
+// two-stage tridiagonalization
+size_t sy2sb_workspace_doubles(i64 n, int b, int num_sms);
+int sy2sb_num_panels(i64 n, int b);
+int sy2sb(Ctx* ctx, i64 n, int b, double* A, i64 lda, double* AB, i64 ldab, double* T1, double* work);
+
 }  // namespace ekb

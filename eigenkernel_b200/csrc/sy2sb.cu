@@ -1,0 +1,311 @@
+// Stage 1 of the two-stage tridiagonalization: dense symmetric -> symmetric band (half bandwidth b).
+// Replaces (together with sb2st.cu) pdsytrd('L') of the reference, src/solver_scalapack_all.f90:59; the
+// two-stage organisation follows the ELPA2 / eigen_sx workflow the reference offers as
+// general_elpa_eigensx (src/solver_elpa_eigenexa.f90:25-198).
+//
+// Per panel p (columns j..j+b-1, rows j+b..n-1, m = n-j-b rows):
+//   1. Householder QR of the m x b panel by ONE cooperative kernel (one grid barrier per column; the
+//      update of column c and the dot products the next reflector needs are fused in a single pass).
+//   2. R and the diagonal block go to band storage AB; V is made explicit in place (unit diagonal, zeros).
+//   3. T (compact WY) from the Gram matrix V^T V.
+//   4. X = A22 V T (SYMM on the DMMA engine reading the lower triangle only), W = X - 1/2 V T^T V^T X.
+//   5. A22 -= [V W][W V]^T  (SYR2K as one K=2b GEMM, lower tiles + one tile diagonal).
+// V stays in A (below the band), T per panel in T1: both are consumed by the back-transformation
+// (ormtr.cu: apply_q1).
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace ekb {
+
+constexpr int QR_THREADS = 256;
+
+// Householder QR of P (m x b, column-major, ld), b <= 64.  Grid of G CTAs, each owning a contiguous row
+// range.  partial: 2 * G * 64 doubles.  Rout: b x b (ld b) receives R (upper triangle); tau: b.
+// In place, rows below the diagonal of column c hold v_c (unit element implicit); the upper triangle of
+// the top b x b block is left stale (fixed by fixup_extract_kernel).
+template <int B>
+__global__ void __launch_bounds__(QR_THREADS) panel_qr_kernel(double* __restrict__ P, i64 ld, int m,
+                                                              double* __restrict__ tau, double* __restrict__ Rout,
+                                                              double* __restrict__ partial) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double red[QR_THREADS / 32][B];
+  __shared__ double g[B];
+  __shared__ double wv[B];
+  __shared__ double s_scal, s_tau;
+  const int G = gridDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rpc = (m + G - 1) / G;
+  const int r0 = blockIdx.x * rpc, r1 = min(m, r0 + rpc);
+  const int kr = min(B, m);
+
+  for (int j = -1; j < kr; ++j) {
+    double scal = 0.0, tj = 0.0;
+    if (j >= 0) {
+      // reduce the partial dot products of column j with columns j..B-1 (rows > j)
+      const double* pp = partial + (size_t)(j & 1) * G * B;
+      if (tid < B) {
+        double s = 0.0;
+        if (tid >= j)
+          for (int q = 0; q < G; ++q) s += pp[q * B + tid];
+        g[tid] = s;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        double alpha = P[(i64)j * ld + j];
+        double xn2 = g[j];
+        double beta, t, sc;
+        if (xn2 == 0.0) {
+          beta = alpha; t = 0.0; sc = 0.0;
+        } else {
+          beta = -copysign(sqrt(alpha * alpha + xn2), alpha);
+          t = (beta - alpha) / beta;
+          sc = 1.0 / (alpha - beta);
+        }
+        s_scal = sc; s_tau = t;
+        if (blockIdx.x == 0) { tau[j] = t; Rout[j * B + j] = beta; }
+      }
+      __syncthreads();
+      scal = s_scal; tj = s_tau;
+      if (tid < B && tid > j) {
+        // w_c = v^T P(:,c) = P(j,c) + scal * g_c ; R(j,c) = P(j,c) - tau * w_c
+        double pjc = P[(i64)tid * ld + j];
+        double w = pjc + scal * g[tid];
+        wv[tid] = tj * w;
+        if (blockIdx.x == 0) Rout[tid * B + j] = pjc - tj * w;
+      }
+      __syncthreads();
+    }
+    // pass over my rows: apply reflector j (if any), then accumulate dots of column j+1 with columns >= j+1
+    double acc[B];
+#pragma unroll
+    for (int c = 0; c < B; ++c) acc[c] = 0.0;
+    const int jn = j + 1;  // next pivot column
+    if (jn < B) {
+      for (int i = r0 + tid; i < r1; i += QR_THREADS) {
+        double vi = 0.0;
+        const bool upd = (j >= 0) && (i > j);
+        if (upd) {
+          vi = P[(i64)j * ld + i] * scal;
+          P[(i64)j * ld + i] = vi;
+        }
+        double p1 = 0.0;
+#pragma unroll
+        for (int c = 0; c < B; ++c) {
+          if (c >= jn) {
+            double x = P[(i64)c * ld + i];
+            if (upd) {
+              x -= wv[c] * vi;
+              P[(i64)c * ld + i] = x;
+            }
+            if (c == jn) p1 = x;
+            if (i > jn) acc[c] += p1 * x;
+          }
+        }
+      }
+    } else if (j >= 0) {
+      // last column: only scale it
+      for (int i = r0 + tid; i < r1; i += QR_THREADS)
+        if (i > j) P[(i64)j * ld + i] *= scal;
+    }
+    if (jn < kr) {
+#pragma unroll
+      for (int c = 0; c < B; ++c) {
+        double v = acc[c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[warp][c] = v;
+      }
+      __syncthreads();
+      if (tid < B) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < QR_THREADS / 32; ++w) s += red[w][tid];
+        partial[(size_t)(jn & 1) * G * B + blockIdx.x * B + tid] = s;
+      }
+    }
+    grid.sync();
+  }
+  // reflectors that do not exist (m < B): tau = 0, R rows beyond m are zero
+  if (blockIdx.x == 0 && tid < B && tid >= kr) tau[tid] = 0.0;
+}
+
+// One CTA per panel: write AB columns j..j+b-1 (diagonal block from A, R from Rout) and make V explicit.
+__global__ void fixup_extract_kernel(double* __restrict__ A, i64 lda, i64 n, i64 j, int b, const double* __restrict__ Rout,
+                                     double* __restrict__ AB, i64 ldab) {
+  const int m = (int)(n - j - b);
+  for (int e = threadIdx.x; e < (int)ldab * b; e += blockDim.x) {
+    int d = e % (int)ldab, c = e / (int)ldab;
+    i64 jc = j + c, i = jc + d;
+    double v = 0.0;
+    if (i < n && d <= b) {
+      if (i < j + b) v = A[jc * lda + i];
+      else {
+        int rr = (int)(i - (j + b));
+        if (rr <= c && rr < m) v = Rout[c * b + rr];
+      }
+    }
+    AB[jc * ldab + d] = v;
+  }
+  double* P = A + j * lda + (j + b);
+  for (int e = threadIdx.x; e < b * b; e += blockDim.x) {
+    int rr = e % b, c = e / b;
+    if (rr < m && rr <= c) P[(i64)c * lda + rr] = (rr == c) ? 1.0 : 0.0;
+  }
+}
+
+// Tail columns (no panel below them): AB(d, jc) = A(jc + d, jc) for d <= b.
+__global__ void extract_tail_kernel(const double* __restrict__ A, i64 lda, i64 n, i64 j0, int b, double* __restrict__ AB,
+                                    i64 ldab) {
+  i64 jc = j0 + blockIdx.x;
+  if (jc >= n) return;
+  for (int d = threadIdx.x; d < ldab; d += blockDim.x) {
+    i64 i = jc + d;
+    AB[jc * ldab + d] = (i < n && d <= b) ? A[jc * lda + i] : 0.0;
+  }
+}
+
+// T = larft(forward, columnwise) from G = V^T V and tau; also usable for any b <= 64.  One CTA of 64 threads.
+__global__ void build_T_kernel(const double* __restrict__ Gm, const double* __restrict__ tau, int b, double* __restrict__ T) {
+  __shared__ double sT[64][65];
+  const int r = threadIdx.x;
+  for (int c = 0; c < b; ++c) {
+    if (r < b) sT[r][c] = 0.0;
+  }
+  __syncthreads();
+  for (int i = 0; i < b; ++i) {
+    const double ti = tau[i];
+    double v = 0.0;
+    if (r < i) {
+      for (int k = r; k < i; ++k) v += sT[r][k] * Gm[i * b + k];
+      v *= -ti;
+    } else if (r == i) v = ti;
+    __syncthreads();
+    if (r <= i && r < b) sT[r][i] = v;
+    __syncthreads();
+  }
+  for (int c = 0; c < b; ++c)
+    if (r < b) T[c * b + r] = sT[r][c];
+}
+
+// TS = T^T * S (b x b), one CTA.
+__global__ void tts_kernel(const double* __restrict__ T, const double* __restrict__ S, int b, double* __restrict__ TS) {
+  for (int e = threadIdx.x; e < b * b; e += blockDim.x) {
+    int r = e % b, c = e / b;
+    double v = 0.0;
+    for (int k = 0; k <= r; ++k) v += T[r * b + k] * S[c * b + k];  // T^T(r,k) = T(k,r), k <= r
+    TS[e] = v;
+  }
+}
+
+// VW = [V | W], WV = [W | V]  (m x 2b, ld = ldp)
+__global__ void pack_vw_kernel(const double* __restrict__ V, i64 ldv, const double* __restrict__ W, i64 ldw, int m, int b,
+                               double* __restrict__ VW, double* __restrict__ WV, i64 ldp) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int c = blockIdx.y;
+  if (i >= m) return;
+  double v = V[(i64)c * ldv + i], w = W[(i64)c * ldw + i];
+  VW[(i64)c * ldp + i] = v;
+  VW[(i64)(c + b) * ldp + i] = w;
+  WV[(i64)c * ldp + i] = w;
+  WV[(i64)(c + b) * ldp + i] = v;
+}
+
+static int pick_splitk(Ctx* ctx, i64 m, i64 n, i64 k, int bm, int bn) {
+  i64 tiles = (i64)cdiv(m, bm) * cdiv(n, bn);
+  i64 want = (2 * ctx->num_sms + tiles - 1) / tiles;
+  i64 maxs = k / 256;
+  if (want > maxs) want = maxs;
+  if (want < 1) want = 1;
+  if (want > 64) want = 64;
+  return (int)want;
+}
+
+// Workspace layout (doubles): see sy2sb_workspace_doubles.
+size_t sy2sb_workspace_doubles(i64 n, int b, int num_sms) {
+  i64 ldp = round_up(n, 8);
+  return (size_t)ldp * b * 2      /* W0/X, (spare) */
+         + (size_t)ldp * 2 * b * 2 /* VW, WV */
+         + (size_t)2 * num_sms * 64 + 8 * 64 * 64;
+}
+
+int sy2sb(Ctx* ctx, i64 n, int b, double* A, i64 lda, double* AB, i64 ldab, double* T1, double* work) {
+  if (n <= 0) return 0;
+  const i64 ldp = round_up(n, 8);
+  double* X = work;                  // m x b
+  double* VW = X + ldp * b * 2;      // m x 2b
+  double* WV = VW + ldp * 2 * b;     // m x 2b
+  double* partial = WV + ldp * 2 * b;
+  double* small = partial + 2 * ctx->num_sms * 64;
+  double* tau = small;               // 64
+  double* Rout = small + 64;         // b*b
+  double* Gm = Rout + 64 * 64;       // b*b
+  double* S = Gm + 64 * 64;          // b*b
+  double* TS = S + 64 * 64;          // b*b
+
+  i64 j = 0;
+  int p = 0;
+  for (;; j += b, ++p) {
+    const i64 m = n - j - b;
+    if (m < 2) break;
+    double* P = A + j * lda + (j + b);
+    double* A22 = A + (j + b) * lda + (j + b);
+    double* T = T1 + (size_t)p * b * b;
+    // 1. panel QR
+    {
+      int G = (int)((m + QR_THREADS - 1) / QR_THREADS);
+      if (G > ctx->num_sms) G = ctx->num_sms;
+      int mi = (int)m;
+      void* args[] = {(void*)&P, (void*)&lda, (void*)&mi, (void*)&tau, (void*)&Rout, (void*)&partial};
+      if (b == 64)
+        EKB_CUDA(cudaLaunchCooperativeKernel((void*)panel_qr_kernel<64>, dim3(G), dim3(QR_THREADS), args, 0, ctx->stream));
+      else
+        EKB_CUDA(cudaLaunchCooperativeKernel((void*)panel_qr_kernel<32>, dim3(G), dim3(QR_THREADS), args, 0, ctx->stream));
+    }
+    // 2. band extraction + explicit V
+    fixup_extract_kernel<<<1, 256, 0, ctx->stream>>>(A, lda, n, j, b, Rout, AB, ldab);
+    EKB_CUDA(cudaGetLastError());
+    // 3. T from Gram matrix
+    GemmP g;
+    g.m = b; g.n = b; g.k = (int)m; g.A = P; g.lda = lda; g.B = P; g.ldb = lda; g.C = Gm; g.ldc = b;
+    g.alpha = 1.0; g.beta = 0.0;
+    EKB_TRY(gemm(ctx, GEMM_TA, g, -1, pick_splitk(ctx, b, b, m, 128, 64)));
+    build_T_kernel<<<1, 64, 0, ctx->stream>>>(Gm, tau, b, T);
+    EKB_CUDA(cudaGetLastError());
+    // 4. W0 = A22 V (symmetric, lower stored) -> VW[:, b:2b) as scratch ; X = W0 T
+    double* W0 = WV;  // scratch m x b
+    g.m = (int)m; g.n = b; g.k = (int)m; g.A = A22; g.lda = lda; g.B = P; g.ldb = lda; g.C = W0; g.ldc = ldp;
+    EKB_TRY(gemm(ctx, GEMM_SYMA, g, -1, pick_splitk(ctx, m, b, m, 128, 64)));
+    g.m = (int)m; g.n = b; g.k = b; g.A = W0; g.lda = ldp; g.B = T; g.ldb = b; g.C = X; g.ldc = ldp;
+    EKB_TRY(gemm(ctx, 0, g));
+    // S = V^T X ; TS = T^T S ; X -= 1/2 V TS   (X becomes W)
+    g.m = b; g.n = b; g.k = (int)m; g.A = P; g.lda = lda; g.B = X; g.ldb = ldp; g.C = S; g.ldc = b;
+    EKB_TRY(gemm(ctx, GEMM_TA, g, -1, pick_splitk(ctx, b, b, m, 128, 64)));
+    tts_kernel<<<1, 256, 0, ctx->stream>>>(T, S, b, TS);
+    EKB_CUDA(cudaGetLastError());
+    g.m = (int)m; g.n = b; g.k = b; g.A = P; g.lda = lda; g.B = TS; g.ldb = b; g.C = X; g.ldc = ldp;
+    g.alpha = -0.5; g.beta = 1.0;
+    EKB_TRY(gemm(ctx, 0, g));
+    // 5. A22 -= [V W][W V]^T
+    pack_vw_kernel<<<dim3(cdiv(m, 256), b), 256, 0, ctx->stream>>>(P, lda, X, ldp, (int)m, b, VW, WV, ldp);
+    EKB_CUDA(cudaGetLastError());
+    g.m = (int)m; g.n = (int)m; g.k = 2 * b; g.A = VW; g.lda = ldp; g.B = WV; g.ldb = ldp; g.C = A22; g.ldc = lda;
+    g.alpha = -1.0; g.beta = 1.0;
+    EKB_TRY(gemm(ctx, GEMM_TB, g, /*tri_keep=*/128));
+  }
+  // tail columns
+  if (j < n) {
+    extract_tail_kernel<<<(unsigned)(n - j), 128, 0, ctx->stream>>>(A, lda, n, j, b, AB, ldab);
+    EKB_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+int sy2sb_num_panels(i64 n, int b) {
+  int p = 0;
+  for (i64 j = 0; n - j - b >= 2; j += b) ++p;
+  return p;
+}
+
+}  // namespace ekb

@@ -74,6 +74,15 @@ int ekb200_sygst(ekb200_ctx* ctx, int64_t n, double* dev_A, int64_t lda, const d
 int ekb200_trtrs_lt(ekb200_ctx* ctx, int64_t n, int64_t nrhs, const double* dev_L, int64_t ldl, double* dev_Z,
                     int64_t ldz);
 
+/* ekb200_sy2sb: first half of pdsytrd('L') (solver_scalapack_all.f90:59) in its two-stage form: dense -> band.
+ *   A (full symmetric on entry) is overwritten: the Householder panels V_p (explicit unit-lower-trapezoidal)
+ *   stay below the band; dev_T1 receives the (b x b) compact-WY factors, one per panel
+ *   (ekb200_sy2sb_num_panels of them); dev_AB (ldab >= 2b rows, n columns) receives the band in lower band
+ *   storage AB(i-j, j) = A(i,j), rows b+1..ldab-1 zeroed (room for the bulges of ekb200_sb2st). */
+int ekb200_sy2sb(ekb200_ctx* ctx, int64_t n, double* dev_A, int64_t lda, double* dev_AB, int64_t ldab, double* dev_T1);
+int ekb200_sy2sb_num_panels(const ekb200_ctx* ctx, int64_t n);
+int ekb200_get_band(const ekb200_ctx* ctx);
+
 /* ---- measurement helper (roofline denominator; never on the solve path) */
 int ekb200_measure_fp64_peak(ekb200_ctx* ctx, double* dmma_tflops, double* dfma_tflops);
 
