@@ -51,6 +51,8 @@ _SIGS = {
     "ekb200_sy2sb": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p],
     "ekb200_sy2sb_num_panels": [c_void_p, c_int64],
     "ekb200_get_band": [c_void_p],
+    "ekb200_sb2st": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p],
+    "ekb200_sb2st_max_tasks": [c_void_p, c_int64],
     "ekb200_measure_fp64_peak": [c_void_p, POINTER(c_double), POINTER(c_double)],
 }
 _RESTYPE = {"ekb200_strerror": c_char_p, "ekb200_last_error": c_char_p}

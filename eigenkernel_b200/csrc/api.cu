@@ -259,6 +259,25 @@ int ekb200_sy2sb(ekb200_ctx* h, int64_t n, double* A, int64_t lda, double* AB, i
   return rc;
 }
 
+int ekb200_sb2st_max_tasks(const ekb200_ctx* h, int64_t n) { return h ? sb2st_max_tasks(n, h->c.band) : 0; }
+
+int ekb200_sb2st(ekb200_ctx* h, int64_t n, double* AB, int64_t ldab, double* V2, int64_t ldv, double* TAU2,
+                 int64_t ldtau, double* d, double* e) {
+  CHECK_CTX(h);
+  if (n < 0) return -2;
+  if (ldab < 2 * ctx->band) return -4;
+  if (ldv < n) return -6;
+  if (ldtau < sb2st_max_tasks(n, ctx->band)) return -8;
+  if (n == 0) return 0;
+  int* prog = nullptr;
+  EKB_TRY(ctx_alloc(ctx, (void**)&prog, (size_t)(n + 8) * sizeof(int)));
+  int rc = sb2st(ctx, n, ctx->band, AB, ldab, V2, ldv, TAU2, (int)ldtau, prog, d, e);
+  cudaError_t ce = cudaStreamSynchronize(ctx->stream);
+  ctx_free(ctx, prog);
+  if (rc == 0) EKB_CUDA(ce);
+  return rc;
+}
+
 int ekb200_measure_fp64_peak(ekb200_ctx* h, double* dmma_tflops, double* dfma_tflops) {
   CHECK_CTX(h);
   if (!dmma_tflops) return -2;

@@ -115,5 +115,8 @@ int sygst_lower(Ctx* ctx, i64 n, double* A, i64 lda, const double* L, i64 ldl, c
 size_t sy2sb_workspace_doubles(i64 n, int b, int num_sms);
 int sy2sb_num_panels(i64 n, int b);
 int sy2sb(Ctx* ctx, i64 n, int b, double* A, i64 lda, double* AB, i64 ldab, double* T1, double* work);
+int sb2st_max_tasks(i64 n, int b);
+int sb2st(Ctx* ctx, i64 n, int b, double* AB, i64 ldab, double* V2, i64 ldv, double* TAU2, int ldtau, int* prog,
+          double* d, double* e);
 
 }  // namespace ekb

@@ -81,6 +81,13 @@ int ekb200_trtrs_lt(ekb200_ctx* ctx, int64_t n, int64_t nrhs, const double* dev_
  *   storage AB(i-j, j) = A(i,j), rows b+1..ldab-1 zeroed (room for the bulges of ekb200_sb2st). */
 int ekb200_sy2sb(ekb200_ctx* ctx, int64_t n, double* dev_A, int64_t lda, double* dev_AB, int64_t ldab, double* dev_T1);
 int ekb200_sy2sb_num_panels(const ekb200_ctx* ctx, int64_t n);
+/* ekb200_sb2st: second half of pdsytrd('L') + the d/e gather (solver_scalapack_all.f90:59,75-78): band ->
+ *   tridiagonal by bulge chasing.  dev_AB is destroyed.  dev_d (n), dev_e (n-1) receive the tridiagonal.
+ *   dev_V2 (ldv >= n rows, n columns): column s = concatenated Householder vectors of sweep s (task t at rows
+ *   s+1+t*b.., leading 1 stored); dev_TAU2 (ldtau = ekb200_sb2st_max_tasks rows, n columns): TAU2(t, s). */
+int ekb200_sb2st(ekb200_ctx* ctx, int64_t n, double* dev_AB, int64_t ldab, double* dev_V2, int64_t ldv,
+                 double* dev_TAU2, int64_t ldtau, double* dev_d, double* dev_e);
+int ekb200_sb2st_max_tasks(const ekb200_ctx* ctx, int64_t n);
 int ekb200_get_band(const ekb200_ctx* ctx);
 
 /* ---- measurement helper (roofline denominator; never on the solve path) */

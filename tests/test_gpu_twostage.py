@@ -56,3 +56,59 @@ def test_sy2sb_band_is_orthogonally_similar(ctx, n, band):
     ctx.set_option("band", 64)
     for d in (dA, dAB, dT):
         d.free()
+
+
+def q2_from_reflectors(V2, TAU2, n, b):
+    """Q2 = prod_{s ascending} prod_{t ascending} H(s,t)."""
+    Q = np.eye(n)
+    for s in range(n - 2):
+        t = 0
+        while True:
+            r0 = s + 1 + t * b
+            nr = min(b, n - r0)
+            if nr < 2:
+                break
+            v = V2[r0:r0 + nr, s]
+            tau = TAU2[t, s]
+            Q[:, r0:r0 + nr] -= tau * np.outer(Q[:, r0:r0 + nr] @ v, v)
+            t += 1
+    return Q
+
+
+def _run_sb2st(ctx, Bd, n, b):
+    AB = np.zeros((2 * b, n), order="F")
+    for d in range(min(b, n - 1) + 1):
+        AB[d, : n - d] = np.diagonal(Bd, -d)
+    dAB = ctx.from_numpy(AB)
+    dV2 = ctx.matrix(n, n)
+    ntm = ctx.lib.ekb200_sb2st_max_tasks(ctx.h, n)
+    dTAU = ctx.matrix(ntm, n)
+    dd, de = ctx.matrix(n, 1), ctx.matrix(n, 1)
+    assert ctx.call("ekb200_sb2st", n, dAB.ptr, dAB.ld, dV2.ptr, dV2.ld, dTAU.ptr, dTAU.ld, dd.ptr, de.ptr) == 0
+    d = dd.download()[:, 0]
+    e = de.download()[: n - 1, 0]
+    out = d, e, dV2.download(), dTAU.download()
+    for x in (dAB, dV2, dTAU, dd, de):
+        x.free()
+    return out
+
+
+@pytest.mark.parametrize("n,band", [(3, 64), (40, 64), (66, 64), (130, 64), (200, 32), (333, 64), (1000, 64)])
+def test_sb2st_tridiagonal_is_orthogonally_similar(ctx, n, band):
+    ctx.set_option("band", band)
+    b = band
+    rng = np.random.default_rng(n)
+    M = rng.standard_normal((n, n))
+    M = M + M.T
+    Bd = np.triu(np.tril(M, b), -b)
+    d, e, V2, TAU2 = _run_sb2st(ctx, Bd, n, b)
+    ctx.set_option("band", 64)
+    T = np.diag(d) + np.diag(e, 1) + np.diag(e, -1)
+    w_ref = np.linalg.eigvalsh(Bd)
+    w = np.linalg.eigvalsh(T)
+    anorm = np.abs(w_ref).max()
+    assert np.max(np.abs(w - w_ref)) <= 1e-13 * n * anorm
+    if n <= 340:
+        Q = q2_from_reflectors(V2, TAU2, n, b)
+        assert np.max(np.abs(Q.T @ Q - np.eye(n))) <= 1e-13 * n
+        assert np.max(np.abs(Q.T @ Bd @ Q - T)) <= 1e-13 * n * anorm
