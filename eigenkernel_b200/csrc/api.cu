@@ -278,6 +278,20 @@ int ekb200_sb2st(ekb200_ctx* h, int64_t n, double* AB, int64_t ldab, double* V2,
   return rc;
 }
 
+int ekb200_stedc(ekb200_ctx* h, int64_t n, double* d, double* e, double* w, double* Z, int64_t ldz, double* merge_flops) {
+  CHECK_CTX(h);
+  if (n < 0) return -2;
+  if (ldz < n) return -7;
+  if (n == 0) return 0;
+  void* work = nullptr;
+  EKB_TRY(ctx_alloc(ctx, &work, stedc_workspace_bytes(n)));
+  int rc = stedc(ctx, n, d, e, w, Z, ldz, work, merge_flops);
+  cudaError_t ce = cudaStreamSynchronize(ctx->stream);
+  ctx_free(ctx, work);
+  if (rc == 0) EKB_CUDA(ce);
+  return rc;
+}
+
 int ekb200_measure_fp64_peak(ekb200_ctx* h, double* dmma_tflops, double* dfma_tflops) {
   CHECK_CTX(h);
   if (!dmma_tflops) return -2;

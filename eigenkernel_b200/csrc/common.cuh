@@ -119,4 +119,7 @@ int sb2st_max_tasks(i64 n, int b);
 int sb2st(Ctx* ctx, i64 n, int b, double* AB, i64 ldab, double* V2, i64 ldv, double* TAU2, int ldtau, int* prog,
           double* d, double* e);
 
+size_t stedc_workspace_bytes(i64 n);
+int stedc(Ctx* ctx, i64 n, double* d, double* e, double* w, double* Z, i64 ldz, void* work, double* flops_out);
+
 }  // namespace ekb

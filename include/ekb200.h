@@ -90,6 +90,13 @@ int ekb200_sb2st(ekb200_ctx* ctx, int64_t n, double* dev_AB, int64_t ldab, doubl
 int ekb200_sb2st_max_tasks(const ekb200_ctx* ctx, int64_t n);
 int ekb200_get_band(const ekb200_ctx* ctx);
 
+/* ekb200_stedc: pdstedc('I') (solver_scalapack_all.f90:96-98): eigen-decomposition of the symmetric tridiagonal
+ *   (dev_d, dev_e), both destroyed.  dev_w (n) ascending eigenvalues, dev_Z (n x n) orthonormal eigenvectors.
+ *   info > 0: that many leaf problems failed to converge.  merge_flops (host, may be NULL): actual FLOPs of the
+ *   merge GEMMs after deflation. */
+int ekb200_stedc(ekb200_ctx* ctx, int64_t n, double* dev_d, double* dev_e, double* dev_w, double* dev_Z, int64_t ldz,
+                 double* merge_flops);
+
 /* ---- measurement helper (roofline denominator; never on the solve path) */
 int ekb200_measure_fp64_peak(ekb200_ctx* ctx, double* dmma_tflops, double* dfma_tflops);
 

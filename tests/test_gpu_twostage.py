@@ -112,3 +112,44 @@ def test_sb2st_tridiagonal_is_orthogonally_similar(ctx, n, band):
         Q = q2_from_reflectors(V2, TAU2, n, b)
         assert np.max(np.abs(Q.T @ Q - np.eye(n))) <= 1e-13 * n
         assert np.max(np.abs(Q.T @ Bd @ Q - T)) <= 1e-13 * n * anorm
+
+
+def _tridiag_cases():
+    rng = np.random.default_rng(7)
+    cases = []
+    for n in (1, 2, 3, 31, 32, 33, 64, 100, 257, 1000, 2500):
+        cases.append((f"rand{n}", rng.standard_normal(n), rng.standard_normal(max(n - 1, 0))))
+    n = 501
+    cases.append(("toeplitz", np.zeros(n), np.ones(n - 1)))                       # heavy deflation
+    m = 200
+    cases.append(("wilkinson", np.abs(np.arange(-m, m + 1)).astype(float), np.ones(2 * m)))  # close pairs
+    e = rng.standard_normal(399)
+    e[[50, 51, 199, 300]] = 0.0
+    cases.append(("split", rng.standard_normal(400), e))                           # exact zeros on cuts or not
+    cases.append(("graded", 10.0 ** (-np.arange(300) / 20.0), 10.0 ** (-np.arange(299) / 20.0 - 1)))
+    cases.append(("negrho", rng.standard_normal(640), -np.abs(rng.standard_normal(639))))
+    cases.append(("identity", np.ones(300), np.zeros(299)))
+    cases.append(("glued", np.tile(np.r_[np.arange(10.0), np.arange(10.0)[::-1]], 16), np.r_[np.ones(319)] * 1e-8 + 1.0))
+    return cases
+
+
+@pytest.mark.parametrize("name,d,e", _tridiag_cases(), ids=[c[0] for c in _tridiag_cases()])
+def test_stedc_matches_oracle(ctx, name, d, e):
+    import ctypes
+    n = d.shape[0]
+    w_ref, Z_ref, info = lt.stedc_I(d, e)
+    assert info == 0
+    dd, de = ctx.from_numpy(d), ctx.from_numpy(np.r_[e, 0.0])
+    dw, dZ = ctx.matrix(n, 1), ctx.matrix(n, n)
+    fl = ctypes.c_double()
+    assert ctx.call("ekb200_stedc", n, dd.ptr, de.ptr, dw.ptr, dZ.ptr, dZ.ld, ctypes.byref(fl)) == 0
+    w = dw.download()[:, 0]
+    Z = dZ.download()
+    T = np.diag(d) + np.diag(e, 1) + np.diag(e, -1)
+    tn = max(np.abs(w_ref).max(), 1e-300)
+    assert np.all(np.diff(w) >= 0)
+    assert np.max(np.abs(w - w_ref)) <= 1e-14 * max(n, 10) * tn
+    assert np.max(np.abs(T @ Z - Z * w[None, :])) <= 1e-14 * max(n, 10) * tn
+    assert np.max(np.abs(Z.T @ Z - np.eye(n))) <= 1e-14 * max(n, 10)
+    for x in (dd, de, dw, dZ):
+        x.free()
