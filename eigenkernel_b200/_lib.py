@@ -54,9 +54,21 @@ _SIGS = {
     "ekb200_stedc": [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, POINTER(c_double)],
     "ekb200_sb2st": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p],
     "ekb200_sb2st_max_tasks": [c_void_p, c_int64],
+    "ekb200_apply_q2": [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64],
+    "ekb200_apply_q1": [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64],
+    "ekb200_syevd_dev": [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64],
+    "ekb200_sygvd_dev": [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p,
+                         c_int64],
+    "ekb200_syevd": [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64],
+    "ekb200_sygvd": [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64],
+    "ekb200_sygvd_coo": [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
+                         c_void_p, c_void_p, c_int64],
+    "ekb200_last_merge_flops": [c_void_p],
+    "ekb200_host_alloc": [c_void_p, c_int64, POINTER(c_void_p)],
+    "ekb200_host_free": [c_void_p, c_void_p],
     "ekb200_measure_fp64_peak": [c_void_p, POINTER(c_double), POINTER(c_double)],
 }
-_RESTYPE = {"ekb200_strerror": c_char_p, "ekb200_last_error": c_char_p}
+_RESTYPE = {"ekb200_strerror": c_char_p, "ekb200_last_error": c_char_p, "ekb200_last_merge_flops": c_double}
 
 
 def exported_symbols():

@@ -11,6 +11,7 @@ struct ekb200_ctx {
   Ctx c;
   double* invd = nullptr;  // inverted 64x64 diagonal blocks of the current Cholesky factor
   i64 invd_n = 0;
+  double merge_flops = 0.0;  // actual FLOPs of the D&C merge GEMMs of the last solve
 };
 
 namespace ekb {
@@ -290,6 +291,198 @@ int ekb200_stedc(ekb200_ctx* h, int64_t n, double* d, double* e, double* w, doub
   ctx_free(ctx, work);
   if (rc == 0) EKB_CUDA(ce);
   return rc;
+}
+
+int ekb200_apply_q2(ekb200_ctx* h, int64_t n, int64_t nrhs, const double* V2, int64_t ldv, const double* TAU2,
+                    int64_t ldtau, double* Z, int64_t ldz) {
+  CHECK_CTX(h);
+  if (n < 0) return -2;
+  if (nrhs < 0) return -3;
+  if (ldv < n) return -5;
+  if (ldtau < sb2st_max_tasks(n, ctx->band)) return -7;
+  if (ldz < n) return -9;
+  if (n == 0 || nrhs == 0) return 0;
+  return apply_q2(ctx, n, ctx->band, V2, ldv, TAU2, (int)ldtau, nrhs, Z, ldz);
+}
+
+int ekb200_apply_q1(ekb200_ctx* h, int64_t n, int64_t nrhs, double* A, int64_t lda, const double* T1, double* Z,
+                    int64_t ldz) {
+  CHECK_CTX(h);
+  if (n < 0) return -2;
+  if (nrhs < 0) return -3;
+  if (lda < n) return -5;
+  if (ldz < n) return -8;
+  if (n == 0 || nrhs == 0) return 0;
+  double* work = nullptr;
+  EKB_TRY(ctx_alloc(ctx, (void**)&work, apply_q1_workspace_doubles(n, ctx->band, nrhs) * sizeof(double)));
+  int rc = apply_q1(ctx, n, ctx->band, A, lda, T1, nrhs, Z, ldz, work);
+  cudaError_t ce = cudaStreamSynchronize(ctx->stream);
+  ctx_free(ctx, work);
+  if (rc == 0) EKB_CUDA(ce);
+  return rc;
+}
+
+int ekb200_host_alloc(ekb200_ctx* h, int64_t bytes, void** p) {
+  CHECK_CTX(h);
+  if (bytes < 0) return -2;
+  if (!p) return -3;
+  *p = nullptr;
+  cudaError_t e = cudaHostAlloc(p, (size_t)(bytes > 0 ? bytes : 16), cudaHostAllocDefault);
+  if (e != cudaSuccess) {
+    ctx->last_cuda = e;
+    ctx->last_error = std::string("cudaHostAlloc: ") + cudaGetErrorString(e);
+    cudaGetLastError();
+    return EKB_ERR_NOMEM;
+  }
+  return 0;
+}
+int ekb200_host_free(ekb200_ctx* h, void* p) {
+  CHECK_CTX(h);
+  if (p) cudaFreeHost(p);
+  return 0;
+}
+
+int ekb200_syevd_dev(ekb200_ctx* h, int64_t n, int64_t nev, double* A, int64_t lda, double* w, double* Z,
+                     int64_t ldz) {
+  CHECK_CTX(h);
+  if (n < 0) return -2;
+  if (nev < 0 || nev > n) return -3;
+  if (lda < n) return -5;
+  if (ldz < n) return -8;
+  h->merge_flops = 0.0;
+  return syevd_dev(ctx, n, nev, A, lda, w, Z, ldz, &h->merge_flops);
+}
+
+int ekb200_sygvd_dev(ekb200_ctx* h, int64_t n, int64_t nev, double* A, int64_t lda, double* B, int64_t ldb, double* w,
+                     double* Z, int64_t ldz) {
+  CHECK_CTX(h);
+  if (n < 0) return -2;
+  if (nev < 0 || nev > n) return -3;
+  if (lda < n) return -5;
+  if (ldb < n) return -7;
+  if (ldz < n) return -10;
+  if (n == 0) return 0;
+  EKB_TRY(ensure_invd(h, n));
+  h->merge_flops = 0.0;
+  return sygvd_dev(ctx, n, nev, A, lda, B, ldb, w, Z, ldz, h->invd, &h->merge_flops);
+}
+
+double ekb200_last_merge_flops(const ekb200_ctx* h) { return h ? h->merge_flops : 0.0; }
+
+// Shared body of the host-pointer front doors.  Exactly one of (A, cooA) describes A; B/cooB likewise
+// (generalized iff hasB).  Host matrices: lower triangles referenced (the reference passes 'L' everywhere).
+struct CooIn {
+  int64_t nnz;
+  const int32_t* ij;
+  const double* v;
+};
+static int solve_host(ekb200_ctx* h, int64_t n, int64_t nev, const double* A, int64_t lda, const CooIn* cooA, bool hasB,
+                      const double* B, int64_t ldb, const CooIn* cooB, double* w, double* Z, int64_t ldz) {
+  Ctx* ctx = &h->c;
+  if (n == 0 || nev == 0) return 0;
+  const i64 ld = round_up(n, 8);
+  double *dA = nullptr, *dB = nullptr, *dZ = nullptr, *dw = nullptr;
+  auto cleanup = [&]() {
+    cudaStreamSynchronize(ctx->stream);
+    ctx_free(ctx, dA); ctx_free(ctx, dB); ctx_free(ctx, dZ); ctx_free(ctx, dw);
+  };
+  int rc = ctx_alloc(ctx, (void**)&dA, (size_t)ld * n * 8);
+  if (!rc && hasB) rc = ctx_alloc(ctx, (void**)&dB, (size_t)ld * n * 8);
+  if (!rc) rc = ctx_alloc(ctx, (void**)&dZ, (size_t)ld * nev * 8);
+  if (!rc) rc = ctx_alloc(ctx, (void**)&dw, (size_t)(n + 8) * 8);
+  if (rc) { cleanup(); return rc; }
+  {
+    StageTimer t(ctx, hasB ? "solve_with_general_b200:setup_matrices" : "eigen_solver_b200:setup_matrices");
+    cudaError_t ce = cudaSuccess;
+    if (cooA) {
+      rc = ekb200_coo_to_dense(h, n, cooA->nnz, cooA->ij, cooA->v, dA, ld);
+    } else {
+      ce = cudaMemcpy2DAsync(dA, ld * 8, A, lda * 8, n * 8, n, cudaMemcpyHostToDevice, ctx->stream);
+      if (ce == cudaSuccess) rc = symmetrize_from_lower(ctx, dA, ld, n);
+    }
+    if (!rc && ce == cudaSuccess && hasB) {
+      if (cooB) {
+        rc = ekb200_coo_to_dense(h, n, cooB->nnz, cooB->ij, cooB->v, dB, ld);
+      } else {
+        ce = cudaMemcpy2DAsync(dB, ld * 8, B, ldb * 8, n * 8, n, cudaMemcpyHostToDevice, ctx->stream);
+        if (ce == cudaSuccess) rc = symmetrize_from_lower(ctx, dB, ld, n);
+      }
+    }
+    if (ce != cudaSuccess) {
+      ctx->last_cuda = ce;
+      ctx->last_error = std::string("h2d: ") + cudaGetErrorString(ce);
+      rc = EKB_ERR_CUDA;
+    }
+    t.stop();
+  }
+  if (!rc) {
+    h->merge_flops = 0.0;
+    if (hasB) {
+      rc = ensure_invd(h, n);
+      if (!rc) rc = sygvd_dev(ctx, n, nev, dA, ld, dB, ld, dw, dZ, ld, h->invd, &h->merge_flops);
+    } else {
+      rc = syevd_dev(ctx, n, nev, dA, ld, dw, dZ, ld, &h->merge_flops);
+    }
+  }
+  if (!rc) {
+    StageTimer t(ctx, hasB ? "solve_with_general_b200:d2h" : "eigen_solver_b200:d2h");
+    cudaError_t ce = cudaMemcpyAsync(w, dw, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (ce == cudaSuccess)
+      ce = cudaMemcpy2DAsync(Z, ldz * 8, dZ, ld * 8, n * 8, nev, cudaMemcpyDeviceToHost, ctx->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
+    t.stop();
+    if (ce != cudaSuccess) {
+      ctx->last_cuda = ce;
+      ctx->last_error = std::string("d2h: ") + cudaGetErrorString(ce);
+      rc = EKB_ERR_CUDA;
+    }
+  }
+  cleanup();
+  return rc;
+}
+
+int ekb200_syevd(ekb200_ctx* h, int64_t n, int64_t nev, const double* A, int64_t lda, double* w, double* Z,
+                 int64_t ldz) {
+  CHECK_CTX(h);
+  if (n < 0) return -2;
+  if (nev < 0 || nev > n) return -3;
+  if (n > 0 && !A) return -4;
+  if (lda < n) return -5;
+  if (n > 0 && !w) return -6;
+  if (nev > 0 && !Z) return -7;
+  if (ldz < n) return -8;
+  return solve_host(h, n, nev, A, lda, nullptr, false, nullptr, 0, nullptr, w, Z, ldz);
+}
+
+int ekb200_sygvd(ekb200_ctx* h, int64_t n, int64_t nev, const double* A, int64_t lda, const double* B, int64_t ldb,
+                 double* w, double* Z, int64_t ldz) {
+  CHECK_CTX(h);
+  if (n < 0) return -2;
+  if (nev < 0 || nev > n) return -3;
+  if (n > 0 && !A) return -4;
+  if (lda < n) return -5;
+  if (n > 0 && !B) return -6;
+  if (ldb < n) return -7;
+  if (n > 0 && !w) return -8;
+  if (nev > 0 && !Z) return -9;
+  if (ldz < n) return -10;
+  return solve_host(h, n, nev, A, lda, nullptr, true, B, ldb, nullptr, w, Z, ldz);
+}
+
+int ekb200_sygvd_coo(ekb200_ctx* h, int64_t n, int64_t nev, int64_t nnzA, const int32_t* ijA, const double* vA,
+                     int64_t nnzB, const int32_t* ijB, const double* vB, double* w, double* Z, int64_t ldz) {
+  CHECK_CTX(h);
+  if (n < 0) return -2;
+  if (nev < 0 || nev > n) return -3;
+  if (nnzA < 0) return -4;
+  if (nnzA > 0 && (!ijA || !vA)) return -5;
+  if (nnzB < 0) return -7;
+  if (nnzB > 0 && (!ijB || !vB)) return -8;
+  if (n > 0 && !w) return -10;
+  if (nev > 0 && !Z) return -11;
+  if (ldz < n) return -12;
+  CooIn a{nnzA, ijA, vA}, b{nnzB, ijB, vB};
+  return solve_host(h, n, nev, nullptr, 0, &a, nnzB > 0, nullptr, 0, nnzB > 0 ? &b : nullptr, w, Z, ldz);
 }
 
 int ekb200_measure_fp64_peak(ekb200_ctx* h, double* dmma_tflops, double* dfma_tflops) {

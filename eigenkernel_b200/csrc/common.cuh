@@ -67,7 +67,9 @@ struct StageTimer {
   Ctx* ctx;
   const char* name;
   cudaEvent_t a, b;
+  bool done = false;
   StageTimer(Ctx* c, const char* n);
+  ~StageTimer();  // a timer abandoned by an early error return records nothing
   double stop();  // records, synchronises, adds the event; returns seconds
 };
 
@@ -118,6 +120,17 @@ int sy2sb(Ctx* ctx, i64 n, int b, double* A, i64 lda, double* AB, i64 ldab, doub
 int sb2st_max_tasks(i64 n, int b);
 int sb2st(Ctx* ctx, i64 n, int b, double* AB, i64 ldab, double* V2, i64 ldv, double* TAU2, int ldtau, int* prog,
           double* d, double* e);
+
+// back-transformations (ormtr.cu)
+int apply_q2(Ctx* ctx, i64 n, int b, const double* V2, i64 ldv, const double* TAU2, int ldtau, i64 k, double* Z,
+             i64 ldz);
+size_t apply_q1_workspace_doubles(i64 n, int b, i64 k);
+int apply_q1(Ctx* ctx, i64 n, int b, double* A, i64 lda, const double* T1, i64 k, double* Z, i64 ldz, double* work);
+
+// whole-solve drivers (solve.cu)
+int syevd_dev(Ctx* ctx, i64 n, i64 nev, double* A, i64 lda, double* w, double* Z, i64 ldz, double* merge_flops);
+int sygvd_dev(Ctx* ctx, i64 n, i64 nev, double* A, i64 lda, double* B, i64 ldb, double* w, double* Z, i64 ldz,
+              double* invd, double* merge_flops);
 
 size_t stedc_workspace_bytes(i64 n);
 int stedc(Ctx* ctx, i64 n, double* d, double* e, double* w, double* Z, i64 ldz, void* work, double* flops_out);

@@ -44,7 +44,15 @@ StageTimer::StageTimer(Ctx* c, const char* n) : ctx(c), name(n) {
   cudaEventCreate(&b);
   cudaEventRecord(a, ctx->stream);
 }
+StageTimer::~StageTimer() {
+  if (!done) {
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+  }
+}
 double StageTimer::stop() {
+  if (done) return 0.0;
+  done = true;
   cudaEventRecord(b, ctx->stream);
   cudaEventSynchronize(b);
   float ms = 0.f;

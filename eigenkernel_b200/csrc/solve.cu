@@ -1,0 +1,152 @@
+// Whole-solve drivers on device-resident matrices: the B200 twins of
+//   eigen_solver_scalapack_all   (reference src/solver_scalapack_all.f90:19-124): pdsytrd -> gather d,e ->
+//                                pdstedc -> pdormtr, here sy2sb -> sb2st -> stedc -> apply_q2 -> apply_q1;
+//   solve_with_general_scalapack (src/solver_scalapack_all.f90:127-168): reduce_generalized ->
+//                                eigen_solver_scalapack_all -> recovery_generalized;
+//   the `-n` selecting workflows (src/solver_main.f90:59-75) as "D&C on all of T, back-transform nev columns".
+// Every stage is timed with CUDA events on the context stream and recorded under the event names of
+// SURVEY.md 8(b) so the caller can replay them through add_event (src/event_logger.f90:23-65).
+#include "common.cuh"
+
+namespace ekb {
+
+namespace {
+// frees every registered pointer when it leaves scope (after draining the stream)
+struct Scratch {
+  Ctx* ctx;
+  std::vector<void*> ptrs;
+  explicit Scratch(Ctx* c) : ctx(c) {}
+  int get(void** p, size_t bytes) {
+    int rc = ctx_alloc(ctx, p, bytes);
+    if (rc == 0) ptrs.push_back(*p);
+    return rc;
+  }
+  void release(void* p) {
+    for (auto& q : ptrs)
+      if (q == p) {
+        cudaStreamSynchronize(ctx->stream);
+        ctx_free(ctx, p);
+        q = nullptr;
+      }
+  }
+  ~Scratch() {
+    cudaStreamSynchronize(ctx->stream);
+    for (void* p : ptrs)
+      if (p) ctx_free(ctx, p);
+  }
+};
+}  // namespace
+
+// A (n x n, full symmetric, destroyed) -> w (n, ascending), Z (n x nev: eigenvectors of the nev lowest).
+int syevd_dev(Ctx* ctx, i64 n, i64 nev, double* A, i64 lda, double* w, double* Z, i64 ldz, double* merge_flops) {
+  if (n <= 0 || nev <= 0) return 0;
+  const int b = ctx->band;
+  Scratch sc(ctx);
+  StageTimer total(ctx, "eigen_solver_b200");
+  const i64 ldab = 2 * b;
+  const int npan = sy2sb_num_panels(n, b);
+  double *AB = nullptr, *T1 = nullptr, *d = nullptr, *e = nullptr;
+  EKB_TRY(sc.get((void**)&AB, (size_t)ldab * n * sizeof(double)));
+  EKB_TRY(sc.get((void**)&T1, (size_t)(npan > 0 ? npan : 1) * b * b * sizeof(double)));
+  EKB_TRY(sc.get((void**)&d, (size_t)(n + 8) * sizeof(double)));
+  EKB_TRY(sc.get((void**)&e, (size_t)(n + 8) * sizeof(double)));
+  {
+    StageTimer t(ctx, "eigen_solver_b200:sy2sb");
+    double* work = nullptr;
+    EKB_TRY(sc.get((void**)&work, sy2sb_workspace_doubles(n, b, ctx->num_sms) * sizeof(double)));
+    int rc = sy2sb(ctx, n, b, A, lda, AB, ldab, T1, work);
+    t.stop();
+    sc.release(work);
+    if (rc) return rc;
+  }
+  const i64 ldv = round_up(n, 8);
+  const int ldtau = sb2st_max_tasks(n, b);
+  double *V2 = nullptr, *TAU2 = nullptr;
+  EKB_TRY(sc.get((void**)&V2, (size_t)ldv * n * sizeof(double)));
+  EKB_TRY(sc.get((void**)&TAU2, (size_t)ldtau * n * sizeof(double)));
+  {
+    StageTimer t(ctx, "eigen_solver_b200:sb2st");
+    int* prog = nullptr;
+    EKB_TRY(sc.get((void**)&prog, (size_t)(n + 8) * sizeof(int)));
+    EKB_CUDA(cudaMemsetAsync(e, 0, (size_t)(n + 8) * sizeof(double), ctx->stream));
+    int rc = sb2st(ctx, n, b, AB, ldab, V2, ldv, TAU2, ldtau, prog, d, e);
+    t.stop();
+    sc.release(prog);
+    if (rc) return rc;
+  }
+  sc.release(AB);
+  {
+    StageTimer t(ctx, "eigen_solver_b200:stedc");
+    void* work = nullptr;
+    EKB_TRY(sc.get(&work, stedc_workspace_bytes(n)));
+    int rc;
+    if (nev == n) {
+      rc = stedc(ctx, n, d, e, w, Z, ldz, work, merge_flops);
+    } else {
+      double* ZT = nullptr;
+      const i64 ldt = round_up(n, 8);
+      EKB_TRY(sc.get((void**)&ZT, (size_t)ldt * n * sizeof(double)));
+      rc = stedc(ctx, n, d, e, w, ZT, ldt, work, merge_flops);
+      if (rc == 0) rc = copy_matrix(ctx, ZT, ldt, Z, ldz, n, nev);
+      sc.release(ZT);
+    }
+    t.stop();
+    sc.release(work);
+    if (rc) return rc;
+  }
+  {
+    StageTimer t(ctx, "eigen_solver_b200:ormtr_sb2st");
+    int rc = apply_q2(ctx, n, b, V2, ldv, TAU2, ldtau, nev, Z, ldz);
+    t.stop();
+    if (rc) return rc;
+  }
+  sc.release(V2);
+  sc.release(TAU2);
+  {
+    StageTimer t(ctx, "eigen_solver_b200:ormtr_sy2sb");
+    double* work = nullptr;
+    EKB_TRY(sc.get((void**)&work, apply_q1_workspace_doubles(n, b, nev) * sizeof(double)));
+    int rc = apply_q1(ctx, n, b, A, lda, T1, nev, Z, ldz, work);
+    t.stop();
+    sc.release(work);
+    if (rc) return rc;
+  }
+  total.stop();
+  EKB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// A, B full symmetric (B SPD) on the device.  B <- L (lower), A destroyed, w ascending, Z^T B Z = I.
+int sygvd_dev(Ctx* ctx, i64 n, i64 nev, double* A, i64 lda, double* B, i64 ldb, double* w, double* Z, i64 ldz,
+              double* invd, double* merge_flops) {
+  if (n <= 0 || nev <= 0) return 0;
+  StageTimer total(ctx, "solve_with_general_b200");
+  {
+    StageTimer red(ctx, "reduce_generalized_b200");
+    {
+      StageTimer t(ctx, "reduce_generalized_b200:potrf");
+      int rc = potrf_lower(ctx, n, B, ldb, invd);
+      t.stop();
+      if (rc) return rc;  // > 0: order of the leading minor that is not positive definite (info(pdpotrf))
+    }
+    {
+      StageTimer t(ctx, "reduce_generalized_b200:sygst");
+      int rc = sygst_lower(ctx, n, A, lda, B, ldb, invd);
+      t.stop();
+      if (rc) return rc;
+    }
+    red.stop();
+  }
+  EKB_TRY(syevd_dev(ctx, n, nev, A, lda, w, Z, ldz, merge_flops));
+  {
+    StageTimer t(ctx, "recovery_generalized_b200");
+    int rc = trsm_lower(ctx, TRSM_LLT, n, nev, B, ldb, invd, Z, ldz);
+    t.stop();
+    if (rc) return rc;
+  }
+  total.stop();
+  EKB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace ekb

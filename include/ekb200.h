@@ -97,6 +97,46 @@ int ekb200_get_band(const ekb200_ctx* ctx);
 int ekb200_stedc(ekb200_ctx* ctx, int64_t n, double* dev_d, double* dev_e, double* dev_w, double* dev_Z, int64_t ldz,
                  double* merge_flops);
 
+/* ekb200_apply_q2 / ekb200_apply_q1: the two halves of pdormtr('L','L','N') (solver_scalapack_all.f90:115-116):
+ *   Z (n x nrhs) <- Q2 Z with the bulge-chasing reflectors of ekb200_sb2st, then Z <- Q1 Z with the panels
+ *   (V below the band of dev_A, T in dev_T1) of ekb200_sy2sb.  dev_A is modified (explicit zeros). */
+int ekb200_apply_q2(ekb200_ctx* ctx, int64_t n, int64_t nrhs, const double* dev_V2, int64_t ldv, const double* dev_TAU2,
+                    int64_t ldtau, double* dev_Z, int64_t ldz);
+int ekb200_apply_q1(ekb200_ctx* ctx, int64_t n, int64_t nrhs, double* dev_A, int64_t lda, const double* dev_T1,
+                    double* dev_Z, int64_t ldz);
+
+/* ---- whole-solve entry points.
+ * nev = n: all eigenpairs (-s b200 / general_b200); nev < n: the nev lowest (-s b200_select /
+ * general_b200_select, option -n; solver_main.f90:59-75).  w always receives all n eigenvalues ascending
+ * (like `values` of pdsyevx, solver_scalapack_select.f90:45); Z is n x nev.
+ *
+ * Device-resident variants (inputs already in HBM; both triangles of the symmetric matrices must be filled):
+ * ekb200_syevd_dev: eigen_solver_scalapack_all (solver_scalapack_all.f90:19-124).  dev_A destroyed.
+ * ekb200_sygvd_dev: solve_with_general_scalapack (solver_scalapack_all.f90:127-168): dev_B <- L, dev_A
+ *   destroyed, Z^T B Z = I.  info > 0 from the Cholesky step = order of the non-positive leading minor
+ *   (info(pdpotrf), generalized_to_standard.f90:25-30). */
+int ekb200_syevd_dev(ekb200_ctx* ctx, int64_t n, int64_t nev, double* dev_A, int64_t lda, double* dev_w, double* dev_Z,
+                     int64_t ldz);
+int ekb200_sygvd_dev(ekb200_ctx* ctx, int64_t n, int64_t nev, double* dev_A, int64_t lda, double* dev_B, int64_t ldb,
+                     double* dev_w, double* dev_Z, int64_t ldz);
+/* Host-pointer variants = what ek_solver_b200_m binds (1x1 BLACS grid: the local array IS the matrix).
+ * Lower triangles of A and B are referenced ('L' everywhere in the reference); A and B are not modified;
+ * host buffers may be pageable (pinned ones from ekb200_host_alloc transfer faster). */
+int ekb200_syevd(ekb200_ctx* ctx, int64_t n, int64_t nev, const double* A, int64_t lda, double* w, double* Z,
+                 int64_t ldz);
+int ekb200_sygvd(ekb200_ctx* ctx, int64_t n, int64_t nev, const double* A, int64_t lda, const double* B, int64_t ldb,
+                 double* w, double* Z, int64_t ldz);
+/* COO front door = setup_distributed_matrix + distribute_global_sparse_matrix + solve
+ * (solver_scalapack_all.f90:141-144): ij is Fortran suffix(2,nnz), 1-based; nnzB = 0 selects the standard
+ * problem. */
+int ekb200_sygvd_coo(ekb200_ctx* ctx, int64_t n, int64_t nev, int64_t nnzA, const int32_t* ijA, const double* vA,
+                     int64_t nnzB, const int32_t* ijB, const double* vB, double* w, double* Z, int64_t ldz);
+/* actual FLOPs of the D&C merge products of the last solve (after deflation) */
+double ekb200_last_merge_flops(const ekb200_ctx* ctx);
+/* pinned host memory for fast transfers */
+int ekb200_host_alloc(ekb200_ctx* ctx, int64_t bytes, void** host_ptr);
+int ekb200_host_free(ekb200_ctx* ctx, void* host_ptr);
+
 /* ---- measurement helper (roofline denominator; never on the solve path) */
 int ekb200_measure_fp64_peak(ekb200_ctx* ctx, double* dmma_tflops, double* dfma_tflops);
 
