@@ -66,9 +66,14 @@ _SIGS = {
     "ekb200_last_merge_flops": [c_void_p],
     "ekb200_host_alloc": [c_void_p, c_int64, POINTER(c_void_p)],
     "ekb200_host_free": [c_void_p, c_void_p],
+    "ekb200_num_launches": [c_void_p],
+    "ekb200_timer_start": [c_void_p],
+    "ekb200_timer_stop": [c_void_p, POINTER(c_double)],
+    "ekb200_gemm_profile": [c_void_p, POINTER(c_double), POINTER(c_double), POINTER(c_int64)],
     "ekb200_measure_fp64_peak": [c_void_p, POINTER(c_double), POINTER(c_double)],
 }
-_RESTYPE = {"ekb200_strerror": c_char_p, "ekb200_last_error": c_char_p, "ekb200_last_merge_flops": c_double}
+_RESTYPE = {"ekb200_strerror": c_char_p, "ekb200_last_error": c_char_p, "ekb200_last_merge_flops": c_double,
+            "ekb200_num_launches": c_int64}
 
 
 def exported_symbols():

@@ -65,6 +65,9 @@ int ekb200_destroy(ekb200_ctx* h) {
   cudaStreamSynchronize(ctx->stream);
   for (void* p : ctx->allocs) cudaFree(p);
   ctx->allocs.clear();
+  for (cudaEvent_t ev : ctx->prof_events) cudaEventDestroy(ev);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->d_info) cudaFree(ctx->d_info);
   if (ctx->h_info) cudaFreeHost(ctx->h_info);
   cudaStreamDestroy(ctx->stream);
@@ -89,6 +92,12 @@ int ekb200_set_option(ekb200_ctx* h, const char* key, int64_t value) {
   if (!strcmp(key, "band")) {
     if (value != 32 && value != 64) return -3;
     ctx->band = (int)value;
+    return 0;
+  }
+  if (!strcmp(key, "profile_gemm")) {
+    ctx->profile_gemm = value != 0;
+    ctx->prof_used = 0;
+    ctx->prof_flops.clear();
     return 0;
   }
   return -2;
@@ -366,6 +375,38 @@ int ekb200_sygvd_dev(ekb200_ctx* h, int64_t n, int64_t nev, double* A, int64_t l
   h->merge_flops = 0.0;
   return sygvd_dev(ctx, n, nev, A, lda, B, ldb, w, Z, ldz, h->invd, &h->merge_flops);
 }
+
+int ekb200_timer_start(ekb200_ctx* h) {
+  CHECK_CTX(h);
+  if (!ctx->ev0) EKB_CUDA(cudaEventCreate(&ctx->ev0));
+  if (!ctx->ev1) EKB_CUDA(cudaEventCreate(&ctx->ev1));
+  EKB_CUDA(cudaStreamSynchronize(ctx->stream));
+  EKB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+  return 0;
+}
+int ekb200_timer_stop(ekb200_ctx* h, double* seconds) {
+  CHECK_CTX(h);
+  if (!seconds) return -2;
+  if (!ctx->ev0 || !ctx->ev1) return -1;
+  EKB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+  EKB_CUDA(cudaEventSynchronize(ctx->ev1));
+  float ms = 0.f;
+  EKB_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  *seconds = ms * 1e-3;
+  return 0;
+}
+
+int ekb200_gemm_profile(ekb200_ctx* h, double* seconds, double* flops, int64_t* launches) {
+  CHECK_CTX(h);
+  if (!seconds) return -2;
+  if (!flops) return -3;
+  if (!launches) return -4;
+  long long l = 0;
+  int rc = gemm_profile_collect(ctx, seconds, flops, &l);
+  *launches = l;
+  return rc;
+}
+int64_t ekb200_num_launches(const ekb200_ctx* h) { return h ? h->c.launches : 0; }
 
 double ekb200_last_merge_flops(const ekb200_ctx* h) { return h ? h->merge_flops : 0.0; }
 

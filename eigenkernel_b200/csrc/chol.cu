@@ -105,7 +105,7 @@ int trtri_diag_blocks(Ctx* ctx, i64 n, const double* L, i64 ldl, double* invd) {
     EKB_CUDA(cudaFuncSetAttribute(trtri_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LEAF_SMEM));
     attr = true;
   }
-  trtri_blocks_kernel<<<cdiv(n, NB), 64, LEAF_SMEM, ctx->stream>>>(L, ldl, n, invd);
+  trtri_blocks_kernel<<<cdiv(n, NB), 64, LEAF_SMEM, ctx->stream>>>(L, ldl, n, invd); EKB_COUNT_LAUNCH(ctx);
   EKB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -190,7 +190,7 @@ static int potrf_rec(Ctx* ctx, i64 n, double* A, i64 lda, double* invd, i64 goff
       EKB_CUDA(cudaFuncSetAttribute(potrf_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LEAF_SMEM));
       attr = true;
     }
-    potrf_leaf_kernel<<<1, 256, LEAF_SMEM, ctx->stream>>>(A, lda, (int)n, invd, ctx->d_info, (int)goff);
+    potrf_leaf_kernel<<<1, 256, LEAF_SMEM, ctx->stream>>>(A, lda, (int)n, invd, ctx->d_info, (int)goff); EKB_COUNT_LAUNCH(ctx);
     EKB_CUDA(cudaGetLastError());
     return 0;
   }

@@ -40,7 +40,14 @@ struct Ctx {
   // stage timers
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::string last_error;
+  // instrumentation
+  long long launches = 0;             // kernels launched by this context (bench.py: gpu_launches)
+  bool profile_gemm = false;          // per-launch CUDA events around every engine GEMM (roofline evidence)
+  std::vector<cudaEvent_t> prof_events;   // pairs (start, stop), one per profiled launch
+  std::vector<double> prof_flops;         // 2 m n k of that launch
+  size_t prof_used = 0;
 };
+#define EKB_COUNT_LAUNCH(c) ((c)->launches++)
 
 #define EKB_CUDA(call)                                                                      \
   do {                                                                                      \
@@ -96,6 +103,7 @@ enum GemmFlags {
 int gemm(Ctx* ctx, int flags, const GemmP& p, int tri_keep = -1, int splitk = 1);
 // Batched: `batch` is a DEVICE array of nb problems; (max_m, max_n) bound the grid.
 int gemm_batched(Ctx* ctx, int flags, const GemmP* d_batch, int nb, int max_m, int max_n);
+int gemm_profile_collect(Ctx* ctx, double* seconds, double* flops, long long* launches);
 
 // ---------------------------------------------------------------- elementwise helpers (fill.cu)
 int fill_synthetic(Ctx* ctx, double* A, i64 lda, i64 n, uint64_t seed, double offdiag_scale, int diag_mode,

@@ -35,7 +35,7 @@ int fill_synthetic(Ctx* ctx, double* A, i64 lda, i64 n, uint64_t seed, double of
                    double diag_value) {
   if (n <= 0) return 0;
   dim3 grid(cdiv(n, 256), (unsigned)n);
-  fill_synth_kernel<<<grid, 256, 0, ctx->stream>>>(A, lda, n, seed, offdiag_div, diag_mode, diag_value);
+  fill_synth_kernel<<<grid, 256, 0, ctx->stream>>>(A, lda, n, seed, offdiag_div, diag_mode, diag_value); EKB_COUNT_LAUNCH(ctx);
   EKB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -48,7 +48,7 @@ __global__ void set_zero_kernel(double* __restrict__ A, i64 lda, i64 m, i64 n) {
 int set_zero(Ctx* ctx, double* A, i64 lda, i64 m, i64 n) {
   if (m <= 0 || n <= 0) return 0;
   dim3 grid(cdiv(m, 256), (unsigned)(n < 32768 ? n : 32768));
-  set_zero_kernel<<<grid, 256, 0, ctx->stream>>>(A, lda, m, n);
+  set_zero_kernel<<<grid, 256, 0, ctx->stream>>>(A, lda, m, n); EKB_COUNT_LAUNCH(ctx);
   EKB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -61,7 +61,7 @@ __global__ void copy_kernel(const double* __restrict__ A, i64 lda, double* __res
 int copy_matrix(Ctx* ctx, const double* A, i64 lda, double* B, i64 ldb, i64 m, i64 n) {
   if (m <= 0 || n <= 0) return 0;
   dim3 grid(cdiv(m, 256), (unsigned)(n < 32768 ? n : 32768));
-  copy_kernel<<<grid, 256, 0, ctx->stream>>>(A, lda, B, ldb, m, n);
+  copy_kernel<<<grid, 256, 0, ctx->stream>>>(A, lda, B, ldb, m, n); EKB_COUNT_LAUNCH(ctx);
   EKB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -74,7 +74,7 @@ __global__ void identity_kernel(double* __restrict__ A, i64 lda, i64 n) {
 int set_identity(Ctx* ctx, double* A, i64 lda, i64 n) {
   if (n <= 0) return 0;
   dim3 grid(cdiv(n, 256), (unsigned)(n < 32768 ? n : 32768));
-  identity_kernel<<<grid, 256, 0, ctx->stream>>>(A, lda, n);
+  identity_kernel<<<grid, 256, 0, ctx->stream>>>(A, lda, n); EKB_COUNT_LAUNCH(ctx);
   EKB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -93,7 +93,7 @@ __global__ void coo_scatter_kernel(double* __restrict__ A, i64 lda, i64 n, i64 n
 }
 int coo_scatter(Ctx* ctx, double* A, i64 lda, i64 n, i64 nnz, const int32_t* d_ij, const double* d_v) {
   if (nnz <= 0) return 0;
-  coo_scatter_kernel<<<cdiv(nnz, 256), 256, 0, ctx->stream>>>(A, lda, n, nnz, d_ij, d_v);
+  coo_scatter_kernel<<<cdiv(nnz, 256), 256, 0, ctx->stream>>>(A, lda, n, nnz, d_ij, d_v); EKB_COUNT_LAUNCH(ctx);
   EKB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -119,7 +119,7 @@ __global__ void symmetrize_kernel(double* __restrict__ A, i64 lda, i64 n) {
 int symmetrize_from_lower(Ctx* ctx, double* A, i64 lda, i64 n) {
   if (n <= 0) return 0;
   dim3 grid(cdiv(n, 32), cdiv(n, 32));
-  symmetrize_kernel<<<grid, dim3(32, 8), 0, ctx->stream>>>(A, lda, n);
+  symmetrize_kernel<<<grid, dim3(32, 8), 0, ctx->stream>>>(A, lda, n); EKB_COUNT_LAUNCH(ctx);
   EKB_CUDA(cudaGetLastError());
   return 0;
 }

@@ -242,7 +242,7 @@ static int launch_cfg(Ctx* ctx, int flags, const GemmP& p, const GemmP* d_batch,
     attr_set = true;
   }
   dim3 grid(cdiv(max_m, BM), cdiv(max_n, BN), BATCHED ? nb : splitk);
-  kern<<<grid, GEMM_THREADS, smem, ctx->stream>>>(p, d_batch, flags, tri_keep, splitk, ctx->splitk_ws);
+  kern<<<grid, GEMM_THREADS, smem, ctx->stream>>>(p, d_batch, flags, tri_keep, splitk, ctx->splitk_ws); EKB_COUNT_LAUNCH(ctx);
   EKB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -264,6 +264,24 @@ int gemm(Ctx* ctx, int flags, const GemmP& p, int tri_keep, int splitk) {
   }
   if (splitk < 1) splitk = 1;
   int rc;
+  const bool prof = ctx->profile_gemm;
+  if (prof) {
+    if (ctx->prof_used + 2 > ctx->prof_events.size()) {
+      for (int q = 0; q < 2048; ++q) {
+        cudaEvent_t ev;
+        EKB_CUDA(cudaEventCreate(&ev));
+        ctx->prof_events.push_back(ev);
+      }
+    }
+    // algorithmic FLOPs: 2 k per computed element; triangular updates count the kept triangle only
+    double elems = (double)p.m * p.n;
+    if (tri_keep >= 0) {
+      const double mn = p.m < p.n ? p.m : p.n;
+      elems = (double)p.m * p.n - 0.5 * mn * (mn - 1.0);
+    }
+    ctx->prof_flops.push_back(2.0 * p.k * elems);
+    EKB_CUDA(cudaEventRecord(ctx->prof_events[ctx->prof_used], ctx->stream));
+  }
   if (p.n <= 64)
     rc = launch_cfg<128, 64, 32, 32, false>(ctx, flags, p, nullptr, 1, p.m, p.n, tri_keep, splitk);
   else if (p.m <= 64)
@@ -275,8 +293,31 @@ int gemm(Ctx* ctx, int flags, const GemmP& p, int tri_keep, int splitk) {
     i64 tot = (i64)p.m * p.n;
     splitk_reduce_kernel<<<cdiv(tot, 256), 256, 0, ctx->stream>>>(ctx->splitk_ws, splitk, p.m, p.n, p.C, p.ldc,
                                                                  p.alpha, p.beta, tri_keep);
+    EKB_COUNT_LAUNCH(ctx);
     EKB_CUDA(cudaGetLastError());
   }
+  if (prof) {
+    EKB_CUDA(cudaEventRecord(ctx->prof_events[ctx->prof_used + 1], ctx->stream));
+    ctx->prof_used += 2;
+  }
+  return 0;
+}
+
+// Sum of the per-launch device times and algorithmic FLOPs recorded since the last call (profile_gemm mode).
+int gemm_profile_collect(Ctx* ctx, double* seconds, double* flops, long long* launches) {
+  EKB_CUDA(cudaStreamSynchronize(ctx->stream));
+  double s = 0.0, f = 0.0;
+  for (size_t q = 0; q + 1 < ctx->prof_used; q += 2) {
+    float ms = 0.f;
+    EKB_CUDA(cudaEventElapsedTime(&ms, ctx->prof_events[q], ctx->prof_events[q + 1]));
+    s += ms * 1e-3;
+    f += ctx->prof_flops[q / 2];
+  }
+  *seconds = s;
+  *flops = f;
+  *launches = (long long)(ctx->prof_used / 2);
+  ctx->prof_used = 0;
+  ctx->prof_flops.clear();
   return 0;
 }
 

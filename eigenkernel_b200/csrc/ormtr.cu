@@ -326,7 +326,7 @@ static int q2_launch(Ctx* ctx, i64 n, const double* V2, i64 ldv, const double* T
   cudaError_t ce = cudaMemcpyAsync(d_off, off.data(), (size_t)(nS + 1) * sizeof(i64), cudaMemcpyHostToDevice, ctx->stream);
   if (ce == cudaSuccess) {
     const int tmax = q2_num_tasks(n, B, 0);
-    q2_pack_kernel<B, NBS><<<dim3(tmax, nS), 128, 0, ctx->stream>>>(V2, ldv, TAU2, ldtau, n, d_off, packed);
+    q2_pack_kernel<B, NBS><<<dim3(tmax, nS), 128, 0, ctx->stream>>>(V2, ldv, TAU2, ldtau, n, d_off, packed); EKB_COUNT_LAUNCH(ctx);
     ce = cudaGetLastError();
   }
   if (ce == cudaSuccess) {
@@ -334,7 +334,7 @@ static int q2_launch(Ctx* ctx, i64 n, const double* V2, i64 ldv, const double* T
     auto kern = q2_apply_kernel<B, NBS, KC>;
     ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (ce == cudaSuccess) {
-      kern<<<cdiv(k, KC), Q2_THREADS, smem, ctx->stream>>>(packed, d_off, n, nS, Z, ldz, k);
+      kern<<<cdiv(k, KC), Q2_THREADS, smem, ctx->stream>>>(packed, d_off, n, nS, Z, ldz, k); EKB_COUNT_LAUNCH(ctx);
       ce = cudaGetLastError();
     }
   }
@@ -409,10 +409,10 @@ int apply_q1(Ctx* ctx, i64 n, int b, double* A, i64 lda, const double* T1, i64 k
   const i64 ldw = W;
   double* Wk2 = Wk + (size_t)W * round_up(k, 8);
 
-  q1_zero_above_kernel<<<npan, 256, 0, ctx->stream>>>(A, lda, b, npan, Gp);
+  q1_zero_above_kernel<<<npan, 256, 0, ctx->stream>>>(A, lda, b, npan, Gp); EKB_COUNT_LAUNCH(ctx);
   EKB_CUDA(cudaGetLastError());
   EKB_CUDA(cudaMemsetAsync(Tb, 0, (size_t)ng * W * W * sizeof(double), ctx->stream));
-  q1_init_tb_kernel<<<npan, 256, 0, ctx->stream>>>(T1, b, npan, Gp, W, Tb);
+  q1_init_tb_kernel<<<npan, 256, 0, ctx->stream>>>(T1, b, npan, Gp, W, Tb); EKB_COUNT_LAUNCH(ctx);
   EKB_CUDA(cudaGetLastError());
 
   if (Gp > 1) {

@@ -49,7 +49,7 @@ int measure_fp64_peak(Ctx* ctx, double* dmma_tflops, double* dfma_tflops) {
   double best = 0.0;
   for (int rep = 0; rep < 5; ++rep) {
     EKB_CUDA(cudaEventRecord(e0, ctx->stream));
-    dmma_peak_kernel<<<ctas, 256, 0, ctx->stream>>>(d_out, iters);
+    dmma_peak_kernel<<<ctas, 256, 0, ctx->stream>>>(d_out, iters); EKB_COUNT_LAUNCH(ctx);
     EKB_CUDA(cudaEventRecord(e1, ctx->stream));
     EKB_CUDA(cudaEventSynchronize(e1));
     EKB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
@@ -61,7 +61,7 @@ int measure_fp64_peak(Ctx* ctx, double* dmma_tflops, double* dfma_tflops) {
   best = 0.0;
   for (int rep = 0; rep < 5; ++rep) {
     EKB_CUDA(cudaEventRecord(e0, ctx->stream));
-    dfma_peak_kernel<<<ctas, 256, 0, ctx->stream>>>(d_out, iters);
+    dfma_peak_kernel<<<ctas, 256, 0, ctx->stream>>>(d_out, iters); EKB_COUNT_LAUNCH(ctx);
     EKB_CUDA(cudaEventRecord(e1, ctx->stream));
     EKB_CUDA(cudaEventSynchronize(e1));
     EKB_CUDA(cudaEventElapsedTime(&ms, e0, e1));

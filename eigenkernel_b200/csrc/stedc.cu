@@ -503,10 +503,10 @@ int stedc(Ctx* ctx, i64 n, double* d, double* e, double* w, double* Z, i64 ldz, 
   (void)Db;
 
   if (nleaf > 1) {
-    dc_cut_kernel<<<cdiv(nleaf, 256), 256, 0, ctx->stream>>>(d, e, n, nleaf);
+    dc_cut_kernel<<<cdiv(nleaf, 256), 256, 0, ctx->stream>>>(d, e, n, nleaf); EKB_COUNT_LAUNCH(ctx);
     EKB_CUDA(cudaGetLastError());
   }
-  dc_leaf_kernel<<<cdiv(nleaf, 4), 128, 0, ctx->stream>>>(d, e, n, nleaf, Dcur, Qcur, ldcur, ctx->d_info + 1);
+  dc_leaf_kernel<<<cdiv(nleaf, 4), 128, 0, ctx->stream>>>(d, e, n, nleaf, Dcur, Qcur, ldcur, ctx->d_info + 1); EKB_COUNT_LAUNCH(ctx);
   EKB_CUDA(cudaGetLastError());
 
   for (int l = depth - 1; l >= 0; --l) {
@@ -518,21 +518,21 @@ int stedc(Ctx* ctx, i64 n, double* d, double* e, double* w, double* Z, i64 ldz, 
       maxsz = std::max(maxsz, nd.sz);
       maxn1 = std::max(maxn1, std::max(nd.n1, nd.sz - nd.n1));
     }
-    dc_zero_offdiag_kernel<<<dim3(maxsz, cdiv(maxsz, 256), cnt), 256, 0, ctx->stream>>>(nodes, Qcur, ldcur);
-    dc_setup_kernel<<<cnt, 256, 0, ctx->stream>>>(nodes, Dcur, e, Qcur, ldcur, wk);
-    dc_deflate_kernel<<<cnt, 32, 0, ctx->stream>>>(nodes, Dcur, wk);
-    dc_rotate_kernel<<<dim3(cdiv(maxsz, 256), cnt), 256, 0, ctx->stream>>>(nodes, Qcur, ldcur, wk);
-    dc_secular_kernel<<<dim3(cdiv(maxsz, 128), cnt), 128, 0, ctx->stream>>>(nodes, wk);
-    dc_lowner_kernel<<<dim3(maxsz, cnt), 128, 0, ctx->stream>>>(nodes, wk);
+    dc_zero_offdiag_kernel<<<dim3(maxsz, cdiv(maxsz, 256), cnt), 256, 0, ctx->stream>>>(nodes, Qcur, ldcur); EKB_COUNT_LAUNCH(ctx);
+    dc_setup_kernel<<<cnt, 256, 0, ctx->stream>>>(nodes, Dcur, e, Qcur, ldcur, wk); EKB_COUNT_LAUNCH(ctx);
+    dc_deflate_kernel<<<cnt, 32, 0, ctx->stream>>>(nodes, Dcur, wk); EKB_COUNT_LAUNCH(ctx);
+    dc_rotate_kernel<<<dim3(cdiv(maxsz, 256), cnt), 256, 0, ctx->stream>>>(nodes, Qcur, ldcur, wk); EKB_COUNT_LAUNCH(ctx);
+    dc_secular_kernel<<<dim3(cdiv(maxsz, 128), cnt), 128, 0, ctx->stream>>>(nodes, wk); EKB_COUNT_LAUNCH(ctx);
+    dc_lowner_kernel<<<dim3(maxsz, cnt), 128, 0, ctx->stream>>>(nodes, wk); EKB_COUNT_LAUNCH(ctx);
     // U lives in the (not yet written) next-level Q buffer
-    dc_buildU_kernel<<<dim3(maxsz, cnt), 128, 0, ctx->stream>>>(nodes, wk, Qnxt, ldnxt);
-    dc_pack_kernel<<<dim3(maxsz, cdiv(maxn1, 256), cnt), 256, 0, ctx->stream>>>(nodes, wk, Qcur, ldcur, W1, ld);
-    dc_gemm_setup_kernel<<<cdiv(cnt, 128), 128, 0, ctx->stream>>>(nodes, cnt, d_gp, W1, ld, Qnxt, ldnxt, W2, ld);
+    dc_buildU_kernel<<<dim3(maxsz, cnt), 128, 0, ctx->stream>>>(nodes, wk, Qnxt, ldnxt); EKB_COUNT_LAUNCH(ctx);
+    dc_pack_kernel<<<dim3(maxsz, cdiv(maxn1, 256), cnt), 256, 0, ctx->stream>>>(nodes, wk, Qcur, ldcur, W1, ld); EKB_COUNT_LAUNCH(ctx);
+    dc_gemm_setup_kernel<<<cdiv(cnt, 128), 128, 0, ctx->stream>>>(nodes, cnt, d_gp, W1, ld, Qnxt, ldnxt, W2, ld); EKB_COUNT_LAUNCH(ctx);
     EKB_CUDA(cudaGetLastError());
     EKB_TRY(gemm_batched(ctx, 0, d_gp, 2 * cnt, maxn1, maxsz));
-    dc_rank_kernel<<<dim3(cdiv(maxsz, 256), cnt), 256, 0, ctx->stream>>>(nodes, wk, Dnxt);
+    dc_rank_kernel<<<dim3(cdiv(maxsz, 256), cnt), 256, 0, ctx->stream>>>(nodes, wk, Dnxt); EKB_COUNT_LAUNCH(ctx);
     dc_permute_kernel<<<dim3(maxsz, cdiv(maxsz, 256), cnt), 256, 0, ctx->stream>>>(nodes, wk, W2, ld, Qcur, ldcur, Qnxt,
-                                                                                ldnxt);
+                                                                                ldnxt); EKB_COUNT_LAUNCH(ctx);
     EKB_CUDA(cudaGetLastError());
     std::swap(Qcur, Qnxt);
     std::swap(ldcur, ldnxt);

@@ -262,16 +262,17 @@ int sy2sb(Ctx* ctx, i64 n, int b, double* A, i64 lda, double* AB, i64 ldab, doub
         EKB_CUDA(cudaLaunchCooperativeKernel((void*)panel_qr_kernel<64>, dim3(G), dim3(QR_THREADS), args, 0, ctx->stream));
       else
         EKB_CUDA(cudaLaunchCooperativeKernel((void*)panel_qr_kernel<32>, dim3(G), dim3(QR_THREADS), args, 0, ctx->stream));
+      EKB_COUNT_LAUNCH(ctx);
     }
     // 2. band extraction + explicit V
-    fixup_extract_kernel<<<1, 256, 0, ctx->stream>>>(A, lda, n, j, b, Rout, AB, ldab);
+    fixup_extract_kernel<<<1, 256, 0, ctx->stream>>>(A, lda, n, j, b, Rout, AB, ldab); EKB_COUNT_LAUNCH(ctx);
     EKB_CUDA(cudaGetLastError());
     // 3. T from Gram matrix
     GemmP g;
     g.m = b; g.n = b; g.k = (int)m; g.A = P; g.lda = lda; g.B = P; g.ldb = lda; g.C = Gm; g.ldc = b;
     g.alpha = 1.0; g.beta = 0.0;
     EKB_TRY(gemm(ctx, GEMM_TA, g, -1, pick_splitk(ctx, b, b, m, 128, 64)));
-    build_T_kernel<<<1, 64, 0, ctx->stream>>>(Gm, tau, b, T);
+    build_T_kernel<<<1, 64, 0, ctx->stream>>>(Gm, tau, b, T); EKB_COUNT_LAUNCH(ctx);
     EKB_CUDA(cudaGetLastError());
     // 4. W0 = A22 V (symmetric, lower stored) -> VW[:, b:2b) as scratch ; X = W0 T
     double* W0 = WV;  // scratch m x b
@@ -282,13 +283,13 @@ int sy2sb(Ctx* ctx, i64 n, int b, double* A, i64 lda, double* AB, i64 ldab, doub
     // S = V^T X ; TS = T^T S ; X -= 1/2 V TS   (X becomes W)
     g.m = b; g.n = b; g.k = (int)m; g.A = P; g.lda = lda; g.B = X; g.ldb = ldp; g.C = S; g.ldc = b;
     EKB_TRY(gemm(ctx, GEMM_TA, g, -1, pick_splitk(ctx, b, b, m, 128, 64)));
-    tts_kernel<<<1, 256, 0, ctx->stream>>>(T, S, b, TS);
+    tts_kernel<<<1, 256, 0, ctx->stream>>>(T, S, b, TS); EKB_COUNT_LAUNCH(ctx);
     EKB_CUDA(cudaGetLastError());
     g.m = (int)m; g.n = b; g.k = b; g.A = P; g.lda = lda; g.B = TS; g.ldb = b; g.C = X; g.ldc = ldp;
     g.alpha = -0.5; g.beta = 1.0;
     EKB_TRY(gemm(ctx, 0, g));
     // 5. A22 -= [V W][W V]^T
-    pack_vw_kernel<<<dim3(cdiv(m, 256), b), 256, 0, ctx->stream>>>(P, lda, X, ldp, (int)m, b, VW, WV, ldp);
+    pack_vw_kernel<<<dim3(cdiv(m, 256), b), 256, 0, ctx->stream>>>(P, lda, X, ldp, (int)m, b, VW, WV, ldp); EKB_COUNT_LAUNCH(ctx);
     EKB_CUDA(cudaGetLastError());
     g.m = (int)m; g.n = (int)m; g.k = 2 * b; g.A = VW; g.lda = ldp; g.B = WV; g.ldb = ldp; g.C = A22; g.ldc = lda;
     g.alpha = -1.0; g.beta = 1.0;
@@ -296,7 +297,7 @@ int sy2sb(Ctx* ctx, i64 n, int b, double* A, i64 lda, double* AB, i64 ldab, doub
   }
   // tail columns
   if (j < n) {
-    extract_tail_kernel<<<(unsigned)(n - j), 128, 0, ctx->stream>>>(A, lda, n, j, b, AB, ldab);
+    extract_tail_kernel<<<(unsigned)(n - j), 128, 0, ctx->stream>>>(A, lda, n, j, b, AB, ldab); EKB_COUNT_LAUNCH(ctx);
     EKB_CUDA(cudaGetLastError());
   }
   return 0;

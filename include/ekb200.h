@@ -29,7 +29,7 @@ int ekb200_create(ekb200_ctx** ctx, int device);
 int ekb200_destroy(ekb200_ctx* ctx);
 const char* ekb200_strerror(int info);
 const char* ekb200_last_error(const ekb200_ctx* ctx);
-int ekb200_set_option(ekb200_ctx* ctx, const char* key, int64_t value); /* "band" = half bandwidth b */
+int ekb200_set_option(ekb200_ctx* ctx, const char* key, int64_t value); /* "band" = half bandwidth b (32|64); "profile_gemm" = 0|1 */
 int ekb200_version(void);
 
 /* ---- timing table (replaces add_event, src/event_logger.f90:23-65; seconds are CUDA-event times) */
@@ -136,6 +136,15 @@ double ekb200_last_merge_flops(const ekb200_ctx* ctx);
 /* pinned host memory for fast transfers */
 int ekb200_host_alloc(ekb200_ctx* ctx, int64_t bytes, void** host_ptr);
 int ekb200_host_free(ekb200_ctx* ctx, void* host_ptr);
+
+/* ---- instrumentation (bench.py): kernels launched so far by this context; with option "profile_gemm" = 1
+ * every engine GEMM is bracketed by CUDA events and ekb200_gemm_profile returns (and resets) the summed device
+ * seconds, algorithmic FLOPs and launch count of the DMMA GEMM kernel family. */
+int64_t ekb200_num_launches(const ekb200_ctx* ctx);
+/* CUDA-event stopwatch on the context's stream (the stream every kernel of the library is launched on) */
+int ekb200_timer_start(ekb200_ctx* ctx);
+int ekb200_timer_stop(ekb200_ctx* ctx, double* seconds);
+int ekb200_gemm_profile(ekb200_ctx* ctx, double* seconds, double* flops, int64_t* launches);
 
 /* ---- measurement helper (roofline denominator; never on the solve path) */
 int ekb200_measure_fp64_peak(ekb200_ctx* ctx, double* dmma_tflops, double* dfma_tflops);
