@@ -94,6 +94,11 @@ int ekb200_set_option(ekb200_ctx* h, const char* key, int64_t value) {
     ctx->band = (int)value;
     return 0;
   }
+  if (!strcmp(key, "q2_kc")) {
+    if (value != 0 && value != 32 && value != 48) return -3;
+    ctx->q2_kc = (int)value;
+    return 0;
+  }
   if (!strcmp(key, "profile_gemm")) {
     ctx->profile_gemm = value != 0;
     ctx->prof_used = 0;

@@ -40,18 +40,15 @@ struct Q2Geom {
   static constexpr int H = B + NBS - 1;            // rows of a diamond block
   static constexpr int HP = (H + 3) / 4 * 4;       // padded to the MMA k granularity
   static constexpr int LDV = HP + 4;               // smem stride of a V column (== 4 mod 16: conflict free)
-  static constexpr int LDT = NBS + 4;              // smem stride of a T row
-  static constexpr int BLK = NBS * LDV + NBS * LDT;  // doubles per packed block
-  static constexpr int RM = 128;                   // ring modulus of the Z window (>= HP, power of two)
-  static constexpr int LDZ = RM + 4;
-  static_assert(HP <= RM, "window must fit the ring");
-  static_assert(LDV % 16 == 4 && LDT % 16 == 4 && LDZ % 16 == 4, "bank-conflict-free strides");
+  static constexpr int BLK = 2 * NBS * LDV;        // doubles per packed block: V image, then Y = V T^T image
+  static_assert(LDV % 16 == 4, "bank-conflict-free strides");
 };
 
 // ------------------------------------------------------------------------------------------ q2 pack
 // One CTA per diamond block (t = blockIdx.x, S = blockIdx.y): gathers V from V2 with the structural zeros
-// made explicit, forms the NBS x NBS compact-WY factor T (forward, columnwise) and writes both in the
-// shared-memory image consumed by q2_apply_kernel.
+// made explicit, forms the NBS x NBS compact-WY factor T (forward, columnwise), folds it into Y = V T^T
+// (so that G Z = Z - V (Y^T Z) needs two products, not three) and writes V and Y in the shared-memory
+// image consumed by q2_apply_kernel.
 template <int B, int NBS>
 __global__ void __launch_bounds__(128) q2_pack_kernel(const double* __restrict__ V2, i64 ldv,
                                                       const double* __restrict__ TAU2, int ldtau, i64 n,
@@ -112,202 +109,309 @@ __global__ void __launch_bounds__(128) q2_pack_kernel(const double* __restrict__
   }
   double* out = packed + (blk_off[S] + t) * (i64)G::BLK;
   for (int idx = tid; idx < NBS * G::LDV; idx += blockDim.x) out[idx] = Vs[idx];
-  double* outT = out + NBS * G::LDV;
-  for (int idx = tid; idx < NBS * G::LDT; idx += blockDim.x) {
-    const int i = idx / G::LDT, j = idx % G::LDT;
-    outT[idx] = (j < NBS) ? Ts[i][j] : 0.0;
+  // Y(r,i) = sum_{j >= i} V(r,j) T(i,j)
+  double* outY = out + NBS * G::LDV;
+  for (int idx = tid; idx < NBS * G::LDV; idx += blockDim.x) {
+    const int i = idx / G::LDV, r = idx % G::LDV;
+    double y = 0.0;
+    for (int j = i; j < NBS; ++j) y += Vs[j * G::LDV + r] * Ts[i][j];
+    outY[idx] = y;
   }
 }
 
 // ------------------------------------------------------------------------------------------ q2 apply
-constexpr int Q2_THREADS = 256;
+__device__ __forceinline__ void q2_cp_async16(double* smem, const double* g) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(g) : "memory");
+}
+__device__ __forceinline__ void q2_cp_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void q2_cp_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
-template <int B, int NBS, int KC>
-__global__ void __launch_bounds__(Q2_THREADS) q2_apply_kernel(const double* __restrict__ packed,
-                                                             const i64* __restrict__ blk_off, i64 n, int nS,
-                                                             double* __restrict__ Z, i64 ldz, i64 k) {
+// One CTA owns KC = 16 NWN columns of Z and walks every diamond block (S descending, t ascending); two CTAs
+// share an SM so that one CTA's window traffic overlaps the other's tensor-pipe work.  Per block:
+//     W = Y^T Zw   (NBS x KC, K = HP)      Zw -= V W   (HP x KC, K = NBS)
+// both on DMMA.8x8x4 with operands read from bank-conflict-free shared-memory layouts; structural zeros of
+// V and Y are skipped at k4 granularity.  The window of HP rows lives in an exact ring (row -> (row+1) mod
+// HP, which keeps the accumulator row pairs 16-byte aligned).  Operand staging is asynchronous and phase
+// shifted so that no load latency sits on the critical path: V(t) streams into shared memory (cp.async)
+// while product 1 runs, Y(t+1) while product 2 runs, and the B rows of Z that enter the next window are
+// prefetched into registers during both products.  Warp grid 2 (M) x NWN (N); warp tile N = 16.
+template <int B, int NBS, int NWN>
+__global__ void __launch_bounds__(64 * NWN, 2) q2_apply_kernel(const double* __restrict__ packed,
+                                                              const i64* __restrict__ blk_off, i64 n, int nS,
+                                                              double* __restrict__ Z, i64 ldz, i64 k) {
   using G = Q2Geom<B, NBS>;
+  constexpr int THREADS = 64 * NWN;
+  constexpr int KC = 16 * NWN;
+  constexpr int HP = G::HP;
+  constexpr int LDZ = HP + 4;
   constexpr int LDW = NBS + 4;
+  constexpr int IMG = NBS * G::LDV;  // doubles of one operand image (V or Y)
+  static_assert(LDZ % 16 == 4 && LDW % 16 == 4, "bank-conflict-free strides");
+  static_assert(HP % 2 == 0 && IMG % 2 == 0, "16-byte granularity");
   extern __shared__ __align__(16) double sm[];
-  double* Zs = sm;                       // KC x LDZ   ring of Z rows: Zs[c*LDZ + (row & (RM-1))]
-  double* Vs = Zs + KC * G::LDZ;         // NBS x LDV  Vs[i*LDV + r]
-  double* Ts = Vs + NBS * G::LDV;        // NBS x LDT  Ts[i*LDT + j]
-  double* Ws = Ts + NBS * G::LDT;        // KC x LDW   Ws[c*LDW + i]
+  double* Zs = sm;                       // KC x LDZ   ring of Z rows: Zs[c*LDZ + (row+1) mod HP]
+  double* Vs = Zs + KC * LDZ;            // NBS x LDV  Vs[i*LDV + r]
+  double* Ys = Vs + IMG;                 // NBS x LDV  Ys[i*LDV + r]
+  double* Ws = Ys + IMG;                 // KC x LDW   Ws[c*LDW + i]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int lq = lane >> 2, lr = lane & 3;
   const i64 c0 = (i64)blockIdx.x * KC;
   const int ncol = (int)min((i64)KC, k - c0);
   double* Zg = Z + c0 * ldz;
 
-  // warp tiling: 2 (M) x 4 (N) warps
   const int wm = warp & 1, wn = warp >> 1;
-  constexpr int WN = KC / 4;             // columns per warp
-  constexpr int NI = WN / 8;
-  static_assert(KC % 32 == 0, "KC must be a multiple of 32");
-  constexpr int M1 = NBS / 2, MI1 = M1 / 8;        // product 1/2: rows of W per warp
-  constexpr int M3 = G::HP / 2;                     // product 3: rows of the window per warp
-  static_assert(G::HP % 16 == 0, "HP must split over two warps in 8-row tiles");
-  constexpr int MI3 = M3 / 8;
+  constexpr int NI = 2;                             // 16 columns per warp
+  constexpr int M1 = NBS / 2, MI1 = M1 / 8;        // product 1: rows of W per warp
+  constexpr int M3 = HP / 2, MI3 = M3 / 8;         // product 2: rows of the window per warp
+  static_assert(HP % 16 == 0, "HP must split over two warps in 8-row tiles");
+  constexpr int ZPF = (B * KC) / THREADS;          // doubles per thread of the B entering rows
+  static_assert((B * KC) % THREADS == 0, "entering rows split evenly");
 
-  for (int idx = tid; idx < KC * G::LDZ; idx += Q2_THREADS) Zs[idx] = 0.0;
-  __syncthreads();
+  for (int idx = tid; idx < KC * LDZ; idx += THREADS) Zs[idx] = 0.0;
 
   i64 lo = 0, hi = 0;  // rows [lo, hi) of the slab are resident (and dirty) in the ring
 
+  auto ring = [&](i64 row) { return (int)((row + 1) % HP); };
   auto evict = [&](i64 upto) {  // write rows [lo, upto) back
     const int rows = (int)(upto - lo);
     if (rows > 0) {
-      for (int idx = tid; idx < rows * ncol; idx += Q2_THREADS) {
-        const int r = idx % rows, c = idx / rows;
-        const i64 row = lo + r;
-        if (row < n) Zg[(i64)c * ldz + row] = Zs[c * G::LDZ + (int)(row & (G::RM - 1))];
+      const int base = ring(lo);
+      if (rows == B) {
+#pragma unroll 4
+        for (int idx = tid; idx < B * ncol; idx += THREADS) {
+          const int r = idx % B, c = idx / B;
+          int q = base + r;
+          if (q >= HP) q -= HP;
+          if (lo + r < n) Zg[(i64)c * ldz + lo + r] = Zs[c * LDZ + q];
+        }
+      } else {
+        for (int idx = tid; idx < rows * ncol; idx += THREADS) {
+          const int r = idx % rows, c = idx / rows;
+          int q = base + r;
+          if (q >= HP) q -= HP;
+          if (lo + r < n) Zg[(i64)c * ldz + lo + r] = Zs[c * LDZ + q];
+        }
       }
       lo = upto;
     }
   };
-  auto fetch = [&](i64 upto) {  // bring rows [hi, upto) in (zero beyond n)
+  // synchronous fetch of rows [hi, upto) (the HP - B extra rows of a fresh window)
+  auto fetch = [&](i64 upto) {
     const int rows = (int)(upto - hi);
     if (rows > 0) {
-      for (int idx = tid; idx < rows * KC; idx += Q2_THREADS) {
+      const int base = ring(hi);
+      for (int idx = tid; idx < rows * KC; idx += THREADS) {
         const int r = idx % rows, c = idx / rows;
-        const i64 row = hi + r;
+        int q = base + r;
+        if (q >= HP) q -= HP;
         double v = 0.0;
-        if (row < n && c < ncol) v = Zg[(i64)c * ldz + row];
-        Zs[c * G::LDZ + (int)(row & (G::RM - 1))] = v;
+        if (hi + r < n && c < ncol) v = __ldcg(Zg + (i64)c * ldz + hi + r);
+        Zs[c * LDZ + q] = v;
       }
       hi = upto;
     }
   };
 
-  for (int S = nS - 1; S >= 0; --S) {
-    const i64 s0 = (i64)S * NBS;
-    const int ntask = q2_num_tasks(n, B, s0);
-    const double* pk = packed + blk_off[S] * (i64)G::BLK;
-    for (int t = 0; t < ntask; ++t, pk += G::BLK) {
-      const i64 R0 = s0 + 1 + (i64)t * B;
-      // ---- stage operands: packed (V,T) image and the Z window [R0, R0+HP)
-      {
-        const double2* src = reinterpret_cast<const double2*>(pk);
-        double2* dst = reinterpret_cast<double2*>(Vs);
-        for (int idx = tid; idx < G::BLK / 2; idx += Q2_THREADS) dst[idx] = __ldg(src + idx);
-      }
-      if (t == 0) {
-        evict(hi);       // flush the previous sweep block's window
-        lo = hi = R0;
-      } else {
-        evict(R0);
-      }
-      __syncthreads();  // ring slots of evicted rows are reused by the rows fetched next
-      fetch(R0 + G::HP);
-      __syncthreads();
-
-      // ---- product 1: W(i,c) = sum_r V(r,i) Zw(r,c);  rows i of this warp: [wm*M1, wm*M1+M1)
-      {
-        double acc[MI1][NI][2];
+  double zreg[ZPF];
+  i64 pf_row0 = 0;  // first of the B rows of Z held in zreg
+  auto prefetch_z = [&](i64 row0) {
+    pf_row0 = row0;
 #pragma unroll
-        for (int a = 0; a < MI1; ++a)
-#pragma unroll
-          for (int j = 0; j < NI; ++j) acc[a][j][0] = acc[a][j][1] = 0.0;
-        const int i0 = wm * M1;
-        const int kbeg = i0 & ~3, kend = min(G::HP, i0 + M1 + B);  // V(r,i) != 0 only for i <= r < i+B
-        const double* va = Vs + (i0 + lq) * G::LDV + lr;
-        const double* zb = Zs + (wn * WN + lq) * G::LDZ;
-        for (int kk = kbeg; kk < kend; kk += 4) {
-          double af[MI1], bf[NI];
-          const int zr = (int)((R0 + kk + lr) & (G::RM - 1));
-#pragma unroll
-          for (int a = 0; a < MI1; ++a) af[a] = va[a * 8 * G::LDV + kk];
-#pragma unroll
-          for (int j = 0; j < NI; ++j) bf[j] = zb[j * 8 * G::LDZ + zr];
-#pragma unroll
-          for (int a = 0; a < MI1; ++a)
-#pragma unroll
-            for (int j = 0; j < NI; ++j) dmma884_(acc[a][j][0], acc[a][j][1], bf[j], af[a]);
-        }
-#pragma unroll
-        for (int a = 0; a < MI1; ++a)
-#pragma unroll
-          for (int j = 0; j < NI; ++j) {
-            const int i = i0 + a * 8 + 2 * lr, c = wn * WN + j * 8 + lq;
-            *reinterpret_cast<double2*>(Ws + c * LDW + i) = make_double2(acc[a][j][0], acc[a][j][1]);
-          }
-      }
-      __syncthreads();
-      // ---- product 2: W <- T W (T upper triangular)
-      {
-        double acc[MI1][NI][2];
-#pragma unroll
-        for (int a = 0; a < MI1; ++a)
-#pragma unroll
-          for (int j = 0; j < NI; ++j) acc[a][j][0] = acc[a][j][1] = 0.0;
-        const int i0 = wm * M1;
-        const double* ta = Ts + (i0 + lq) * G::LDT + lr;
-        const double* wb = Ws + (wn * WN + lq) * LDW + lr;
-        for (int kk = i0; kk < NBS; kk += 4) {
-          double af[MI1], bf[NI];
-#pragma unroll
-          for (int a = 0; a < MI1; ++a) af[a] = ta[a * 8 * G::LDT + kk];
-#pragma unroll
-          for (int j = 0; j < NI; ++j) bf[j] = wb[j * 8 * LDW + kk];
-#pragma unroll
-          for (int a = 0; a < MI1; ++a)
-#pragma unroll
-            for (int j = 0; j < NI; ++j) dmma884_(acc[a][j][0], acc[a][j][1], bf[j], af[a]);
-        }
-        __syncthreads();  // every warp has finished reading W
-#pragma unroll
-        for (int a = 0; a < MI1; ++a)
-#pragma unroll
-          for (int j = 0; j < NI; ++j) {
-            const int i = i0 + a * 8 + 2 * lr, c = wn * WN + j * 8 + lq;
-            *reinterpret_cast<double2*>(Ws + c * LDW + i) = make_double2(acc[a][j][0], acc[a][j][1]);
-          }
-      }
-      __syncthreads();
-      // ---- product 3: Zw(r,c) -= sum_i V(r,i) W(i,c);  rows r of this warp: [wm*M3, wm*M3+M3)
-      {
-        double acc[MI3][NI][2];
-#pragma unroll
-        for (int a = 0; a < MI3; ++a)
-#pragma unroll
-          for (int j = 0; j < NI; ++j) acc[a][j][0] = acc[a][j][1] = 0.0;
-        const int r0w = wm * M3;
-        const double* va = Vs + lr * G::LDV + r0w + lq;
-        const double* wb = Ws + (wn * WN + lq) * LDW + lr;
-#pragma unroll
-        for (int kk = 0; kk < NBS; kk += 4) {
-          double bf[NI];
-#pragma unroll
-          for (int j = 0; j < NI; ++j) bf[j] = wb[j * 8 * LDW + kk];
-#pragma unroll
-          for (int a = 0; a < MI3; ++a) {
-            // rows [ra, ra+8) of the window see reflectors i with r-B < i <= r only
-            const int ra = r0w + a * 8;
-            if (kk <= ra + 7 && kk + 3 > ra - B) {
-              const double af = va[(i64)kk * G::LDV + a * 8];
-#pragma unroll
-              for (int j = 0; j < NI; ++j) dmma884_(acc[a][j][0], acc[a][j][1], bf[j], af);
-            }
-          }
-        }
-#pragma unroll
-        for (int a = 0; a < MI3; ++a)
-#pragma unroll
-          for (int j = 0; j < NI; ++j) {
-            const int r = r0w + a * 8 + 2 * lr, c = wn * WN + j * 8 + lq;
-            double* zc = Zs + c * G::LDZ;
-            const int q0 = (int)((R0 + r) & (G::RM - 1)), q1 = (int)((R0 + r + 1) & (G::RM - 1));
-            zc[q0] -= acc[a][j][0];
-            zc[q1] -= acc[a][j][1];
-          }
-      }
-      __syncthreads();
+    for (int q = 0; q < ZPF; ++q) {
+      const int idx = tid + q * THREADS;
+      const int r = idx % B, c = idx / B;
+      double v = 0.0;
+      if (row0 + r < n && c < ncol) v = __ldcg(Zg + (i64)c * ldz + row0 + r);
+      zreg[q] = v;
     }
+  };
+  auto commit_z = [&]() {
+    const int base = ring(pf_row0);
+#pragma unroll
+    for (int q = 0; q < ZPF; ++q) {
+      const int idx = tid + q * THREADS;
+      const int r = idx % B, c = idx / B;
+      int p = base + r;
+      if (p >= HP) p -= HP;
+      Zs[c * LDZ + p] = zreg[q];
+    }
+  };
+  auto stream_image = [&](double* dst, const double* src) {  // IMG doubles, 16 bytes per cp.async
+    for (int idx = tid; idx < IMG / 2; idx += THREADS) q2_cp_async16(dst + 2 * idx, src + 2 * idx);
+    q2_cp_commit();
+  };
+
+  // first block of the walk
+  int S = nS - 1;
+  while (S >= 0 && q2_num_tasks(n, B, (i64)S * NBS) == 0) --S;
+  if (S < 0) return;
+  int t = 0;
+  int ntask = q2_num_tasks(n, B, (i64)S * NBS);
+  const double* pk = packed + blk_off[S] * (i64)G::BLK;
+  __syncthreads();
+  stream_image(Ys, pk + IMG);
+  prefetch_z((i64)S * NBS + 1);
+  bool have_pf = true;
+
+  while (S >= 0) {
+    const i64 s0 = (i64)S * NBS;
+    const i64 R0 = s0 + 1 + (i64)t * B;
+    // ---- phase A: retire rows that left the window, bring the entering rows in
+    if (t == 0) {
+      evict(hi);
+      lo = hi = R0;
+    } else {
+      evict(R0);
+    }
+    if (!have_pf) prefetch_z(hi);  // synchronous path (tiny sweep blocks only)
+    q2_cp_wait_all();              // Y(t) has landed
+    __syncthreads();               // (1) ring slots of evicted rows are free; Y visible to all
+    commit_z();
+    hi += B;
+    fetch(R0 + HP);                // no-op except for a fresh window (t == 0): its last HP - B rows
+    stream_image(Vs, pk);          // V(t): needed by product 2 only
+    __syncthreads();               // (2) window complete
+    // ---- next block of the walk; prefetch its entering rows of Z
+    int nS_ = S, nt_ = t + 1;
+    const double* npk = pk + G::BLK;
+    if (nt_ >= ntask) {
+      nS_ = S - 1;
+      nt_ = 0;
+      if (nS_ >= 0) npk = packed + blk_off[nS_] * (i64)G::BLK;
+    }
+    have_pf = false;
+    if (nS_ >= 0) {
+      if (nt_ > 0) {
+        prefetch_z(hi);  // the next window is [R0+B, R0+B+HP): rows [hi, hi+B) enter
+        have_pf = true;
+      } else if (ntask >= 4) {
+        // next sweep block restarts at the top: those rows were evicted >= 2 barriers ago (ntask >= 4)
+        prefetch_z((i64)nS_ * NBS + 1);
+        have_pf = true;
+      }
+    }
+    const int zbase = ring(R0);  // even: R0 is odd
+
+    // ---- product 1: W(i,c) = sum_r Y(r,i) Zw(r,c);  rows i of this warp: [wm*M1, wm*M1+M1)
+    {
+      double acc[MI1][NI][2];
+#pragma unroll
+      for (int a = 0; a < MI1; ++a)
+#pragma unroll
+        for (int j = 0; j < NI; ++j) acc[a][j][0] = acc[a][j][1] = 0.0;
+      const int i0 = wm * M1;
+      const double* ya = Ys + (i0 + lq) * G::LDV + lr;
+      const double* zb = Zs + (wn * 16 + lq) * LDZ;
+#pragma unroll 4
+      for (int kk = i0; kk < HP; kk += 4) {  // Y(r,i) == 0 for r < i
+        double af[MI1], bf[NI];
+        int zr = zbase + kk + lr;
+        if (zr >= HP) zr -= HP;
+#pragma unroll
+        for (int a = 0; a < MI1; ++a) af[a] = ya[a * 8 * G::LDV + kk];
+#pragma unroll
+        for (int j = 0; j < NI; ++j) bf[j] = zb[j * 8 * LDZ + zr];
+#pragma unroll
+        for (int a = 0; a < MI1; ++a)
+#pragma unroll
+          for (int j = 0; j < NI; ++j) dmma884_(acc[a][j][0], acc[a][j][1], bf[j], af[a]);
+      }
+#pragma unroll
+      for (int a = 0; a < MI1; ++a)
+#pragma unroll
+        for (int j = 0; j < NI; ++j) {
+          const int i = i0 + a * 8 + 2 * lr, c = wn * 16 + j * 8 + lq;
+          *reinterpret_cast<double2*>(Ws + c * LDW + i) = make_double2(acc[a][j][0], acc[a][j][1]);
+        }
+    }
+    q2_cp_wait_all();   // V(t) has landed
+    __syncthreads();    // (3) W and V visible; Ys is free
+    if (nS_ >= 0) stream_image(Ys, npk + IMG);  // Y(t+1) streams in under product 2
+    // ---- product 2: Zw(r,c) -= sum_i V(r,i) W(i,c);  rows r of this warp: [wm*M3, wm*M3+M3)
+    {
+      double acc[MI3][NI][2];
+#pragma unroll
+      for (int a = 0; a < MI3; ++a)
+#pragma unroll
+        for (int j = 0; j < NI; ++j) acc[a][j][0] = acc[a][j][1] = 0.0;
+      const int r0w = wm * M3;
+      const double* va = Vs + lr * G::LDV + r0w + lq;
+      const double* wb = Ws + (wn * 16 + lq) * LDW + lr;
+#pragma unroll
+      for (int kk = 0; kk < NBS; kk += 4) {
+        double bf[NI];
+#pragma unroll
+        for (int j = 0; j < NI; ++j) bf[j] = wb[j * 8 * LDW + kk];
+#pragma unroll
+        for (int a = 0; a < MI3; ++a) {
+          // rows [ra, ra+8) of the window see reflectors i with r-B < i <= r only
+          const int ra = r0w + a * 8;
+          if (kk <= ra + 7 && kk + 3 > ra - B) {
+            const double af = va[(i64)kk * G::LDV + a * 8];
+#pragma unroll
+            for (int j = 0; j < NI; ++j) dmma884_(acc[a][j][0], acc[a][j][1], bf[j], af);
+          }
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < MI3; ++a)
+#pragma unroll
+        for (int j = 0; j < NI; ++j) {
+          const int r = r0w + a * 8 + 2 * lr, c = wn * 16 + j * 8 + lq;
+          int q0 = zbase + r;  // even, and q0 + 1 < HP: the pair never straddles the ring seam
+          if (q0 >= HP) q0 -= HP;
+          double2* zp = reinterpret_cast<double2*>(Zs + c * LDZ + q0);
+          double2 zv = *zp;
+          zv.x -= acc[a][j][0];
+          zv.y -= acc[a][j][1];
+          *zp = zv;
+        }
+    }
+    __syncthreads();    // (4) window updated; Vs is free
+    // ---- advance
+    if (nt_ == 0 && nS_ >= 0) ntask = q2_num_tasks(n, B, (i64)nS_ * NBS);
+    S = nS_;
+    t = nt_;
+    pk = npk;
   }
   evict(min(hi, n));
 }
 
-template <int B, int NBS, int KC>
+template <int B, int NBS, int NWN>
+static size_t q2_smem_bytes() {
+  using G = Q2Geom<B, NBS>;
+  constexpr int KC = 16 * NWN;
+  return (size_t)(KC * (G::HP + 4) + G::BLK + KC * (NBS + 4)) * sizeof(double);
+}
+
+// Work per SM is what bounds the walk (every CTA is a serial chain over all diamond blocks): choose the slab
+// width that minimises ceil(#CTA / #SM) * KC, the columns the busiest SM has to process.
+template <int B, int NBS, int NWN>
+static void q2_consider(Ctx* ctx, i64 k, int force_kc, long long* best_cost, int* best_nwn) {
+  constexpr int KC = 16 * NWN;
+  if (force_kc > 0 && force_kc != KC) return;
+  const long long nct = (k + KC - 1) / KC;
+  const long long cost = ((nct + ctx->num_sms - 1) / ctx->num_sms) * KC;
+  if (*best_nwn == 0 || cost < *best_cost || (cost == *best_cost && NWN > *best_nwn)) {
+    *best_cost = cost;
+    *best_nwn = NWN;
+  }
+}
+
+template <int B, int NBS, int NWN>
+static cudaError_t q2_apply_launch(Ctx* ctx, const double* packed, const i64* d_off, i64 n, int nS, double* Z, i64 ldz,
+                                   i64 k) {
+  const size_t smem = q2_smem_bytes<B, NBS, NWN>();
+  auto kern = q2_apply_kernel<B, NBS, NWN>;
+  cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (ce != cudaSuccess) return ce;
+  kern<<<cdiv(k, 16 * NWN), 64 * NWN, smem, ctx->stream>>>(packed, d_off, n, nS, Z, ldz, k);
+  EKB_COUNT_LAUNCH(ctx);
+  return cudaGetLastError();
+}
+
+template <int B, int NBS>
 static int q2_launch(Ctx* ctx, i64 n, const double* V2, i64 ldv, const double* TAU2, int ldtau, i64 k, double* Z,
                      i64 ldz) {
   using G = Q2Geom<B, NBS>;
@@ -326,16 +430,19 @@ static int q2_launch(Ctx* ctx, i64 n, const double* V2, i64 ldv, const double* T
   cudaError_t ce = cudaMemcpyAsync(d_off, off.data(), (size_t)(nS + 1) * sizeof(i64), cudaMemcpyHostToDevice, ctx->stream);
   if (ce == cudaSuccess) {
     const int tmax = q2_num_tasks(n, B, 0);
-    q2_pack_kernel<B, NBS><<<dim3(tmax, nS), 128, 0, ctx->stream>>>(V2, ldv, TAU2, ldtau, n, d_off, packed); EKB_COUNT_LAUNCH(ctx);
+    q2_pack_kernel<B, NBS><<<dim3(tmax, nS), 128, 0, ctx->stream>>>(V2, ldv, TAU2, ldtau, n, d_off, packed);
+    EKB_COUNT_LAUNCH(ctx);
     ce = cudaGetLastError();
   }
   if (ce == cudaSuccess) {
-    constexpr size_t smem = (size_t)(KC * G::LDZ + NBS * G::LDV + NBS * G::LDT + KC * (NBS + 4)) * sizeof(double);
-    auto kern = q2_apply_kernel<B, NBS, KC>;
-    ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (ce == cudaSuccess) {
-      kern<<<cdiv(k, KC), Q2_THREADS, smem, ctx->stream>>>(packed, d_off, n, nS, Z, ldz, k); EKB_COUNT_LAUNCH(ctx);
-      ce = cudaGetLastError();
+    long long cost = 0;
+    int nwn = 0;
+    q2_consider<B, NBS, 2>(ctx, k, ctx->q2_kc, &cost, &nwn);
+    q2_consider<B, NBS, 3>(ctx, k, ctx->q2_kc, &cost, &nwn);
+    switch (nwn) {
+      case 2: ce = q2_apply_launch<B, NBS, 2>(ctx, packed, d_off, n, nS, Z, ldz, k); break;
+      case 3: ce = q2_apply_launch<B, NBS, 3>(ctx, packed, d_off, n, nS, Z, ldz, k); break;
+      default: ce = cudaErrorInvalidValue;
     }
   }
   if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
@@ -351,8 +458,8 @@ static int q2_launch(Ctx* ctx, i64 n, const double* V2, i64 ldv, const double* T
 // Z (n x k) <- Q2 Z with the reflectors produced by sb2st (layout documented there).
 int apply_q2(Ctx* ctx, i64 n, int b, const double* V2, i64 ldv, const double* TAU2, int ldtau, i64 k, double* Z,
              i64 ldz) {
-  if (b == 64) return q2_launch<64, 32, 64>(ctx, n, V2, ldv, TAU2, ldtau, k, Z, ldz);
-  if (b == 32) return q2_launch<32, 32, 64>(ctx, n, V2, ldv, TAU2, ldtau, k, Z, ldz);
+  if (b == 64) return q2_launch<64, 32>(ctx, n, V2, ldv, TAU2, ldtau, k, Z, ldz);
+  if (b == 32) return q2_launch<32, 32>(ctx, n, V2, ldv, TAU2, ldtau, k, Z, ldz);
   return EKB_ERR_INTERNAL;
 }
 
