@@ -37,7 +37,7 @@ struct Ctx {
   int* h_info = nullptr;              // pinned mirror
   // options
   int band = 64;                      // b: half bandwidth of the two-stage reduction
-  int q2_kc = 0;                      // columns of Z per CTA in apply_q2 (0 = choose; 32|48)
+  int q2_kc = 0;                      // columns of Z per CTA in apply_q2 (0 = choose; 64|80|96|112|128)
   // stage timers
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::string last_error;

@@ -8,10 +8,9 @@
 //   ("diamond") block G(S,t) = H(s0,t) ... H(s0+NBS-1,t) = I - V T V^T with V of (b+NBS-1) x NBS.
 //   Valid application order (reflectors (s,t), (s',t') with s < s' only conflict when t' <= t):
 //   sweep blocks S descending, chase steps t ascending.  Columns of Z are independent, so ONE kernel
-//   applies the whole of Q2: a CTA owns KC columns of Z, keeps the moving (b+NBS-1)-row window of its slab
-//   in a shared-memory ring and walks all diamond blocks, three DMMA products per block
-//   (W = V^T Zw, W = T W, Zw -= V W) with structural zeros of V and T skipped at k4 granularity.
-//   The packed (V,T) images are produced once by q2_pack_kernel in exactly the shared-memory layout.
+//   applies the whole of Q2: every warp owns 16 columns of Z, keeps the moving window of its columns in
+//   registers as DMMA accumulator tiles and walks all diamond blocks with two products per block
+//   (W = Y^T Zw with Y = V T^T, then Zw -= V W); see q2_apply_kernel.
 // apply_q1: G panels are aggregated into one (G*b)-wide WY block (T by the block recurrence
 //   T[0:c,c] = -T[0:c,0:c] (V_{<c}^T V_c) T_c), then Z -= V (T (V^T Z)) as three engine GEMMs per group,
 //   groups descending.
@@ -34,27 +33,37 @@ __host__ __device__ __forceinline__ int q2_num_tasks(i64 n, int b, i64 s) {
   return (int)((n - 3 - s) / b) + 1;
 }
 
-// Compile-time geometry of the diamond blocks.
+// Compile-time geometry of the diamond blocks.  Window coordinates r' = row - W0 with W0 = s0 + t*B (a
+// multiple of 8, so 8-row accumulator tiles never straddle a window edge and row pairs are 16-byte aligned);
+// reflector i of the block occupies r' in [i+1, i+B].
 template <int B, int NBS>
 struct Q2Geom {
-  static constexpr int H = B + NBS - 1;            // rows of a diamond block
-  static constexpr int HP = (H + 3) / 4 * 4;       // padded to the MMA k granularity
-  static constexpr int LDV = HP + 4;               // smem stride of a V column (== 4 mod 16: conflict free)
-  static constexpr int BLK = 2 * NBS * LDV;        // doubles per packed block: V image, then Y = V T^T image
-  static_assert(LDV % 16 == 4, "bank-conflict-free strides");
+  static constexpr int HP = B + NBS;               // rows of the window
+  static constexpr int TILES = HP / 8;             // 8-row accumulator tiles of the window
+  static constexpr int SHIFT = B / 8;              // tiles retired (and entering) per chase step
+  static constexpr int MI = NBS / 8;               // 8-reflector tiles of a block
+  static constexpr int LDY = HP + 8;               // Y image: Ys[i*LDY + r']   (K-major in r')
+  static constexpr int LDVT = NBS + 8;             // V image: Vt[r'*LDVT + i]  (K-major in i), holds -V
+  static constexpr int IMG_Y = NBS * LDY;
+  static constexpr int IMG = IMG_Y + HP * LDVT;    // doubles per packed block
+  static_assert(HP % 8 == 0 && B % 8 == 0 && NBS % 8 == 0, "tile granularity");
+  // 128-bit fragment loads are bank-conflict free iff the row stride is 8 mod 16 doubles
+  static_assert(LDY % 16 == 8 && LDVT % 16 == 8, "bank-conflict-free strides");
 };
 
 // ------------------------------------------------------------------------------------------ q2 pack
 // One CTA per diamond block (t = blockIdx.x, S = blockIdx.y): gathers V from V2 with the structural zeros
 // made explicit, forms the NBS x NBS compact-WY factor T (forward, columnwise), folds it into Y = V T^T
-// (so that G Z = Z - V (Y^T Z) needs two products, not three) and writes V and Y in the shared-memory
-// image consumed by q2_apply_kernel.
+// (so that G Z = Z - V (Y^T Z) needs two products, not three) and writes Y and -V as the shared-memory
+// images consumed by q2_apply_kernel.
 template <int B, int NBS>
 __global__ void __launch_bounds__(128) q2_pack_kernel(const double* __restrict__ V2, i64 ldv,
                                                       const double* __restrict__ TAU2, int ldtau, i64 n,
                                                       const i64* __restrict__ blk_off, double* __restrict__ packed) {
   using G = Q2Geom<B, NBS>;
-  __shared__ double Vs[NBS * G::LDV];
+  constexpr int H = B + NBS - 1;   // rows r = r' - 1 of the parallelogram
+  constexpr int LDS_ = H + 2;
+  __shared__ double Vs[NBS * LDS_];  // Vs[i*LDS_ + r]
   __shared__ double Gs[NBS][NBS + 1];
   __shared__ double Ts[NBS][NBS + 1];
   __shared__ double taus[NBS];
@@ -62,11 +71,11 @@ __global__ void __launch_bounds__(128) q2_pack_kernel(const double* __restrict__
   const i64 s0 = (i64)S * NBS;
   if (t >= q2_num_tasks(n, B, s0)) return;
   const i64 R0 = s0 + 1 + (i64)t * B;
-  for (int idx = tid; idx < NBS * G::LDV; idx += blockDim.x) {
-    const int i = idx / G::LDV, r = idx % G::LDV;
+  for (int idx = tid; idx < NBS * LDS_; idx += blockDim.x) {
+    const int i = idx / LDS_, r = idx % LDS_;
     const i64 s = s0 + i;
     double v = 0.0;
-    if (r < G::H && s <= n - 3) {
+    if (r < H && s <= n - 3) {
       const i64 r0 = R0 + i;  // first row of reflector (s, t)
       const i64 nr = min((i64)B, n - r0);
       if (nr >= 2 && r >= i && r < i + nr) v = V2[s * ldv + R0 + r];
@@ -88,9 +97,9 @@ __global__ void __launch_bounds__(128) q2_pack_kernel(const double* __restrict__
     const int i = idx / NBS, j = idx % NBS;
     double g = 0.0;
     if (i < j) {
-      const double* vi = Vs + i * G::LDV;
-      const double* vj = Vs + j * G::LDV;
-      for (int r = j; r < min(G::H, i + B); ++r) g += vi[r] * vj[r];
+      const double* vi = Vs + i * LDS_;
+      const double* vj = Vs + j * LDS_;
+      for (int r = j; r < min(H, i + B); ++r) g += vi[r] * vj[r];
     }
     Gs[i][j] = g;
     Ts[i][j] = 0.0;
@@ -107,306 +116,277 @@ __global__ void __launch_bounds__(128) q2_pack_kernel(const double* __restrict__
     if (tid <= i) Ts[tid][i] = v;
     __syncthreads();
   }
-  double* out = packed + (blk_off[S] + t) * (i64)G::BLK;
-  for (int idx = tid; idx < NBS * G::LDV; idx += blockDim.x) out[idx] = Vs[idx];
-  // Y(r,i) = sum_{j >= i} V(r,j) T(i,j)
-  double* outY = out + NBS * G::LDV;
-  for (int idx = tid; idx < NBS * G::LDV; idx += blockDim.x) {
-    const int i = idx / G::LDV, r = idx % G::LDV;
+  double* out = packed + (blk_off[S] + t) * (i64)G::IMG;
+  // Y image: Y(r,i) = sum_{j >= i} V(r,j) T(i,j), stored at r' = r + 1
+  for (int idx = tid; idx < G::IMG_Y; idx += blockDim.x) {
+    const int i = idx / G::LDY, rp = idx % G::LDY;
     double y = 0.0;
-    for (int j = i; j < NBS; ++j) y += Vs[j * G::LDV + r] * Ts[i][j];
-    outY[idx] = y;
+    if (rp >= 1 && rp - 1 < H) {
+      const int r = rp - 1;
+      for (int j = i; j < NBS; ++j) y += Vs[j * LDS_ + r] * Ts[i][j];
+    }
+    out[idx] = y;
+  }
+  // -V image, transposed
+  double* outV = out + G::IMG_Y;
+  for (int idx = tid; idx < G::HP * G::LDVT; idx += blockDim.x) {
+    const int rp = idx / G::LDVT, i = idx % G::LDVT;
+    double v = 0.0;
+    if (i < NBS && rp >= 1 && rp - 1 < H) v = -Vs[i * LDS_ + rp - 1];
+    outV[idx] = v;
   }
 }
 
 // ------------------------------------------------------------------------------------------ q2 apply
-__device__ __forceinline__ void q2_cp_async16(double* smem, const double* g) {
-  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(g) : "memory");
+// TMA bulk copy (cp.async.bulk, SASS UBLKCP) completing on an mbarrier: one instruction moves a whole block image.
+__device__ __forceinline__ unsigned q2_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void q2_mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(q2_smem_u32(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void q2_cp_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-__device__ __forceinline__ void q2_cp_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+__device__ __forceinline__ void q2_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(q2_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void q2_bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                   q2_smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(q2_smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void q2_mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(q2_smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void q2_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
-// One CTA owns KC = 16 NWN columns of Z and walks every diamond block (S descending, t ascending); two CTAs
-// share an SM so that one CTA's window traffic overlaps the other's tensor-pipe work.  Per block:
-//     W = Y^T Zw   (NBS x KC, K = HP)      Zw -= V W   (HP x KC, K = NBS)
-// both on DMMA.8x8x4 with operands read from bank-conflict-free shared-memory layouts; structural zeros of
-// V and Y are skipped at k4 granularity.  The window of HP rows lives in an exact ring (row -> (row+1) mod
-// HP, which keeps the accumulator row pairs 16-byte aligned).  Operand staging is asynchronous and phase
-// shifted so that no load latency sits on the critical path: V(t) streams into shared memory (cp.async)
-// while product 1 runs, Y(t+1) while product 2 runs, and the B rows of Z that enter the next window are
-// prefetched into registers during both products.  Warp grid 2 (M) x NWN (N); warp tile N = 16.
-template <int B, int NBS, int NWN>
-__global__ void __launch_bounds__(64 * NWN, 2) q2_apply_kernel(const double* __restrict__ packed,
-                                                              const i64* __restrict__ blk_off, i64 n, int nS,
-                                                              double* __restrict__ Z, i64 ldz, i64 k) {
+// One CTA owns 16 NW columns of Z and walks every diamond block (S descending, t ascending).  Each WARP owns 16
+// of those columns and keeps its HP x 16 piece of the moving window in REGISTERS, as DMMA accumulator tiles
+// (thread (lq,lr) holds rows 8 rho + 2 lr + {0,1} of column lq), for the whole walk:
+//     W = Y^T Zw     the Z tiles are used directly as the k-side MMA operand: within an 8-row tile the two
+//                    DMMA.8x8x4 steps take k = {2 lr} and k = {2 lr + 1} (a permutation of the summation
+//                    index applied to both operands), which is exactly what each thread already holds;
+//     Zw += (-V) W   W likewise goes from accumulator layout straight into the k-side operand.
+// So the window never touches shared memory, there is no cross-warp exchange and no barrier between the two
+// products; shared memory only carries the (Y, -V) images of the block (double buffered, each streamed by
+// ONE cp.async.bulk (TMA, mbarrier completion) one block ahead), read with conflict-free 128-bit loads, 0.25 loads per DMMA.  Rows that leave the
+// window are stored from registers, rows that enter are prefetched into registers one step ahead.  Every
+// global element is always touched by the same thread, so program order is all the ordering the walk needs.
+template <int B, int NBS, int NW, bool AL16>
+__global__ void __launch_bounds__(32 * NW, 1) q2_apply_kernel(const double* __restrict__ packed,
+                                                             const i64* __restrict__ blk_off, i64 n, int nS,
+                                                             double* __restrict__ Z, i64 ldz, i64 k) {
   using G = Q2Geom<B, NBS>;
-  constexpr int THREADS = 64 * NWN;
-  constexpr int KC = 16 * NWN;
-  constexpr int HP = G::HP;
-  constexpr int LDZ = HP + 4;
-  constexpr int LDW = NBS + 4;
-  constexpr int IMG = NBS * G::LDV;  // doubles of one operand image (V or Y)
-  static_assert(LDZ % 16 == 4 && LDW % 16 == 4, "bank-conflict-free strides");
-  static_assert(HP % 2 == 0 && IMG % 2 == 0, "16-byte granularity");
-  extern __shared__ __align__(16) double sm[];
-  double* Zs = sm;                       // KC x LDZ   ring of Z rows: Zs[c*LDZ + (row+1) mod HP]
-  double* Vs = Zs + KC * LDZ;            // NBS x LDV  Vs[i*LDV + r]
-  double* Ys = Vs + IMG;                 // NBS x LDV  Ys[i*LDV + r]
-  double* Ws = Ys + IMG;                 // KC x LDW   Ws[c*LDW + i]
+  constexpr int TILES = G::TILES, SHIFT = G::SHIFT, KEEP = TILES - SHIFT, MI = G::MI;
+  constexpr int LDY = G::LDY, LDVT = G::LDVT, IMG = G::IMG;
+  static_assert(KEEP >= 0 && KEEP <= SHIFT && IMG % 2 == 0, "geometry");
+  extern __shared__ __align__(16) double sm[];  // two image buffers
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int lq = lane >> 2, lr = lane & 3;
-  const i64 c0 = (i64)blockIdx.x * KC;
-  const int ncol = (int)min((i64)KC, k - c0);
-  double* Zg = Z + c0 * ldz;
-
-  const int wm = warp & 1, wn = warp >> 1;
-  constexpr int NI = 2;                             // 16 columns per warp
-  constexpr int M1 = NBS / 2, MI1 = M1 / 8;        // product 1: rows of W per warp
-  constexpr int M3 = HP / 2, MI3 = M3 / 8;         // product 2: rows of the window per warp
-  static_assert(HP % 16 == 0, "HP must split over two warps in 8-row tiles");
-  constexpr int ZPF = (B * KC) / THREADS;          // doubles per thread of the B entering rows
-  static_assert((B * KC) % THREADS == 0, "entering rows split evenly");
-
-  for (int idx = tid; idx < KC * LDZ; idx += THREADS) Zs[idx] = 0.0;
-
-  i64 lo = 0, hi = 0;  // rows [lo, hi) of the slab are resident (and dirty) in the ring
-
-  auto ring = [&](i64 row) { return (int)((row + 1) % HP); };
-  auto evict = [&](i64 upto) {  // write rows [lo, upto) back
-    const int rows = (int)(upto - lo);
-    if (rows > 0) {
-      const int base = ring(lo);
-      if (rows == B) {
-#pragma unroll 4
-        for (int idx = tid; idx < B * ncol; idx += THREADS) {
-          const int r = idx % B, c = idx / B;
-          int q = base + r;
-          if (q >= HP) q -= HP;
-          if (lo + r < n) Zg[(i64)c * ldz + lo + r] = Zs[c * LDZ + q];
-        }
-      } else {
-        for (int idx = tid; idx < rows * ncol; idx += THREADS) {
-          const int r = idx % rows, c = idx / rows;
-          int q = base + r;
-          if (q >= HP) q -= HP;
-          if (lo + r < n) Zg[(i64)c * ldz + lo + r] = Zs[c * LDZ + q];
-        }
-      }
-      lo = upto;
-    }
-  };
-  // synchronous fetch of rows [hi, upto) (the HP - B extra rows of a fresh window)
-  auto fetch = [&](i64 upto) {
-    const int rows = (int)(upto - hi);
-    if (rows > 0) {
-      const int base = ring(hi);
-      for (int idx = tid; idx < rows * KC; idx += THREADS) {
-        const int r = idx % rows, c = idx / rows;
-        int q = base + r;
-        if (q >= HP) q -= HP;
-        double v = 0.0;
-        if (hi + r < n && c < ncol) v = __ldcg(Zg + (i64)c * ldz + hi + r);
-        Zs[c * LDZ + q] = v;
-      }
-      hi = upto;
-    }
-  };
-
-  double zreg[ZPF];
-  i64 pf_row0 = 0;  // first of the B rows of Z held in zreg
-  auto prefetch_z = [&](i64 row0) {
-    pf_row0 = row0;
+  const i64 cwarp = (i64)blockIdx.x * (16 * NW) + 16 * warp;  // first column of this warp
+  const bool cols_full = cwarp + 16 <= k;                     // warp-uniform
+  double* zc[2];
+  bool cv[2];
 #pragma unroll
-    for (int q = 0; q < ZPF; ++q) {
-      const int idx = tid + q * THREADS;
-      const int r = idx % B, c = idx / B;
-      double v = 0.0;
-      if (row0 + r < n && c < ncol) v = __ldcg(Zg + (i64)c * ldz + row0 + r);
-      zreg[q] = v;
+  for (int j = 0; j < 2; ++j) {
+    cv[j] = cwarp + lq + 8 * j < k;
+    zc[j] = Z + (cv[j] ? (cwarp + lq + 8 * j) * ldz : 0) + 2 * lr;  // row offset 2 lr folded in
+  }
+  // rows (row, row+1) of this thread's column j, row = tile row + 2 lr (even).  FAST: no bounds checks.
+  auto ld2 = [&](i64 trow, int j, bool fast) -> double2 {
+    const double* p = zc[j] + trow;
+    if (fast) {
+      if (AL16) return __ldcg(reinterpret_cast<const double2*>(p));
+      return make_double2(__ldcg(p), __ldcg(p + 1));
     }
-  };
-  auto commit_z = [&]() {
-    const int base = ring(pf_row0);
-#pragma unroll
-    for (int q = 0; q < ZPF; ++q) {
-      const int idx = tid + q * THREADS;
-      const int r = idx % B, c = idx / B;
-      int p = base + r;
-      if (p >= HP) p -= HP;
-      Zs[c * LDZ + p] = zreg[q];
+    double2 v = make_double2(0.0, 0.0);
+    const i64 row = trow + 2 * lr;
+    if (cv[j]) {
+      if (row < n) v.x = __ldcg(p);
+      if (row + 1 < n) v.y = __ldcg(p + 1);
     }
+    return v;
   };
-  auto stream_image = [&](double* dst, const double* src) {  // IMG doubles, 16 bytes per cp.async
-    for (int idx = tid; idx < IMG / 2; idx += THREADS) q2_cp_async16(dst + 2 * idx, src + 2 * idx);
-    q2_cp_commit();
+  auto st2 = [&](i64 trow, int j, bool fast, double x, double y) {
+    double* p = zc[j] + trow;
+    if (fast) {
+      if (AL16) *reinterpret_cast<double2*>(p) = make_double2(x, y);
+      else { p[0] = x; p[1] = y; }
+      return;
+    }
+    const i64 row = trow + 2 * lr;
+    if (cv[j]) {
+      if (row < n) p[0] = x;
+      if (row + 1 < n) p[1] = y;
+    }
   };
 
-  // first block of the walk
+  __shared__ unsigned long long bars[2];
+  constexpr unsigned IMG_BYTES = IMG * sizeof(double);
+  static_assert(IMG_BYTES % 16 == 0, "bulk copies move multiples of 16 bytes");
+  if (tid == 0) {
+    q2_mbar_init(&bars[0], 1);
+    q2_mbar_init(&bars[1], 1);
+    q2_fence_proxy_async();
+  }
+  __syncthreads();
+  auto stream_image = [&](int b, const double* src) {  // one elected thread; completion lands on bars[b]
+    if (tid == 0) {
+      q2_fence_proxy_async();
+      q2_mbar_expect_tx(&bars[b], IMG_BYTES);
+      q2_bulk_g2s(sm + b * IMG, src, IMG_BYTES, &bars[b]);
+    }
+  };
+  unsigned phase = 0;  // bit b: parity to wait for on bars[b]
+
+  double zacc[TILES][2][2];   // the window
+  double zin[SHIFT][2][2];    // rows entering at the next step
+
   int S = nS - 1;
   while (S >= 0 && q2_num_tasks(n, B, (i64)S * NBS) == 0) --S;
   if (S < 0) return;
-  int t = 0;
-  int ntask = q2_num_tasks(n, B, (i64)S * NBS);
-  const double* pk = packed + blk_off[S] * (i64)G::BLK;
-  __syncthreads();
-  stream_image(Ys, pk + IMG);
-  prefetch_z((i64)S * NBS + 1);
-  bool have_pf = true;
+  stream_image(0, packed + blk_off[S] * (i64)IMG);
+  int buf = 0;
 
-  while (S >= 0) {
+  for (; S >= 0; --S) {
     const i64 s0 = (i64)S * NBS;
-    const i64 R0 = s0 + 1 + (i64)t * B;
-    // ---- phase A: retire rows that left the window, bring the entering rows in
-    if (t == 0) {
-      evict(hi);
-      lo = hi = R0;
-    } else {
-      evict(R0);
-    }
-    if (!have_pf) prefetch_z(hi);  // synchronous path (tiny sweep blocks only)
-    q2_cp_wait_all();              // Y(t) has landed
-    __syncthreads();               // (1) ring slots of evicted rows are free; Y visible to all
-    commit_z();
-    hi += B;
-    fetch(R0 + HP);                // no-op except for a fresh window (t == 0): its last HP - B rows
-    stream_image(Vs, pk);          // V(t): needed by product 2 only
-    __syncthreads();               // (2) window complete
-    // ---- next block of the walk; prefetch its entering rows of Z
-    int nS_ = S, nt_ = t + 1;
-    const double* npk = pk + G::BLK;
-    if (nt_ >= ntask) {
-      nS_ = S - 1;
-      nt_ = 0;
-      if (nS_ >= 0) npk = packed + blk_off[nS_] * (i64)G::BLK;
-    }
-    have_pf = false;
-    if (nS_ >= 0) {
-      if (nt_ > 0) {
-        prefetch_z(hi);  // the next window is [R0+B, R0+B+HP): rows [hi, hi+B) enter
-        have_pf = true;
-      } else if (ntask >= 4) {
-        // next sweep block restarts at the top: those rows were evicted >= 2 barriers ago (ntask >= 4)
-        prefetch_z((i64)nS_ * NBS + 1);
-        have_pf = true;
-      }
-    }
-    const int zbase = ring(R0);  // even: R0 is odd
-
-    // ---- product 1: W(i,c) = sum_r Y(r,i) Zw(r,c);  rows i of this warp: [wm*M1, wm*M1+M1)
+    const int ntask = q2_num_tasks(n, B, s0);
+    const double* pk = packed + blk_off[S] * (i64)IMG;
+    // ---- fresh window [s0, s0 + HP).  The "+ 0.0" makes the loads complete HERE (a real consumer), so the
+    // walk below never waits on a scoreboard shared with its own prefetch loads.
     {
-      double acc[MI1][NI][2];
+      const bool fast = cols_full && s0 + G::HP <= n;
 #pragma unroll
-      for (int a = 0; a < MI1; ++a)
+      for (int r = 0; r < TILES; ++r)
 #pragma unroll
-        for (int j = 0; j < NI; ++j) acc[a][j][0] = acc[a][j][1] = 0.0;
-      const int i0 = wm * M1;
-      const double* ya = Ys + (i0 + lq) * G::LDV + lr;
-      const double* zb = Zs + (wn * 16 + lq) * LDZ;
-#pragma unroll 4
-      for (int kk = i0; kk < HP; kk += 4) {  // Y(r,i) == 0 for r < i
-        double af[MI1], bf[NI];
-        int zr = zbase + kk + lr;
-        if (zr >= HP) zr -= HP;
-#pragma unroll
-        for (int a = 0; a < MI1; ++a) af[a] = ya[a * 8 * G::LDV + kk];
-#pragma unroll
-        for (int j = 0; j < NI; ++j) bf[j] = zb[j * 8 * LDZ + zr];
-#pragma unroll
-        for (int a = 0; a < MI1; ++a)
-#pragma unroll
-          for (int j = 0; j < NI; ++j) dmma884_(acc[a][j][0], acc[a][j][1], bf[j], af[a]);
-      }
-#pragma unroll
-      for (int a = 0; a < MI1; ++a)
-#pragma unroll
-        for (int j = 0; j < NI; ++j) {
-          const int i = i0 + a * 8 + 2 * lr, c = wn * 16 + j * 8 + lq;
-          *reinterpret_cast<double2*>(Ws + c * LDW + i) = make_double2(acc[a][j][0], acc[a][j][1]);
+        for (int j = 0; j < 2; ++j) {
+          const double2 v = ld2(s0 + 8 * r, j, fast);
+          zacc[r][j][0] = v.x + 0.0;
+          zacc[r][j][1] = v.y + 0.0;
         }
     }
-    q2_cp_wait_all();   // V(t) has landed
-    __syncthreads();    // (3) W and V visible; Ys is free
-    if (nS_ >= 0) stream_image(Ys, npk + IMG);  // Y(t+1) streams in under product 2
-    // ---- product 2: Zw(r,c) -= sum_i V(r,i) W(i,c);  rows r of this warp: [wm*M3, wm*M3+M3)
-    {
-      double acc[MI3][NI][2];
+    for (int t = 0; t < ntask; ++t, pk += IMG) {
+      const i64 W0 = s0 + (i64)t * B;
+      const bool last = t + 1 >= ntask;
+      q2_mbar_wait(&bars[buf], (phase >> buf) & 1u);  // this block's images have landed (streamed one block ahead)
+      phase ^= 1u << buf;
+      __syncthreads();    // every warp is done with the other buffer
+      const double* Ys = sm + buf * IMG;
+      const double* Vt = Ys + G::IMG_Y;
+      if (!last) stream_image(buf ^ 1, pk + IMG);
+      else if (S > 0) stream_image(buf ^ 1, packed + blk_off[S - 1] * (i64)IMG);
+      if (!last) {        // rows entering the next window of this sweep block
+        const bool fast = cols_full && W0 + G::HP + B <= n;
 #pragma unroll
-      for (int a = 0; a < MI3; ++a)
+        for (int q = 0; q < SHIFT; ++q)
 #pragma unroll
-        for (int j = 0; j < NI; ++j) acc[a][j][0] = acc[a][j][1] = 0.0;
-      const int r0w = wm * M3;
-      const double* va = Vs + lr * G::LDV + r0w + lq;
-      const double* wb = Ws + (wn * 16 + lq) * LDW + lr;
-#pragma unroll
-      for (int kk = 0; kk < NBS; kk += 4) {
-        double bf[NI];
-#pragma unroll
-        for (int j = 0; j < NI; ++j) bf[j] = wb[j * 8 * LDW + kk];
-#pragma unroll
-        for (int a = 0; a < MI3; ++a) {
-          // rows [ra, ra+8) of the window see reflectors i with r-B < i <= r only
-          const int ra = r0w + a * 8;
-          if (kk <= ra + 7 && kk + 3 > ra - B) {
-            const double af = va[(i64)kk * G::LDV + a * 8];
-#pragma unroll
-            for (int j = 0; j < NI; ++j) dmma884_(acc[a][j][0], acc[a][j][1], bf[j], af);
+          for (int j = 0; j < 2; ++j) {
+            const double2 v = ld2(W0 + G::HP + 8 * q, j, fast);
+            zin[q][j][0] = v.x;
+            zin[q][j][1] = v.y;
           }
+      }
+      // ---- product 1: W(i,c) = sum_r' Y(r',i) Zw(r',c)
+      double wacc[MI][2][2];
+#pragma unroll
+      for (int a = 0; a < MI; ++a)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) wacc[a][j][0] = wacc[a][j][1] = 0.0;
+      {
+        const double* yp = Ys + lq * LDY + 2 * lr;
+#pragma unroll
+        for (int r = 0; r < TILES; ++r)
+#pragma unroll
+          for (int a = 0; a < MI; ++a)
+            if (r >= a) {  // Y(r',i) == 0 for r' <= i
+              const double2 y = *reinterpret_cast<const double2*>(yp + a * 8 * LDY + 8 * r);
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                dmma884_(wacc[a][j][0], wacc[a][j][1], zacc[r][j][0], y.x);
+                dmma884_(wacc[a][j][0], wacc[a][j][1], zacc[r][j][1], y.y);
+              }
+            }
+      }
+      // ---- product 2: Zw(r',c) += sum_i (-V)(r',i) W(i,c)
+      {
+        const double* vp = Vt + lq * LDVT + 2 * lr;
+#pragma unroll
+        for (int a = 0; a < MI; ++a)
+#pragma unroll
+          for (int r = 0; r < TILES; ++r)
+            if (r >= a && r <= a + B / 8) {  // V(r',i) != 0 only for i < r' <= i + B
+              const double2 v = *reinterpret_cast<const double2*>(vp + r * 8 * LDVT + 8 * a);
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                dmma884_(zacc[r][j][0], zacc[r][j][1], wacc[a][j][0], v.x);
+                dmma884_(zacc[r][j][0], zacc[r][j][1], wacc[a][j][1], v.y);
+              }
+            }
+      }
+      // ---- retire the rows that leave the window, shift, take the entering rows
+      {
+        const bool fast = cols_full && W0 + G::HP <= n;
+        if (!last) {
+#pragma unroll
+          for (int r = 0; r < SHIFT; ++r)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) st2(W0 + 8 * r, j, fast, zacc[r][j][0], zacc[r][j][1]);
+#pragma unroll
+          for (int r = 0; r < KEEP; ++r)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              zacc[r][j][0] = zacc[r + SHIFT][j][0];
+              zacc[r][j][1] = zacc[r + SHIFT][j][1];
+            }
+#pragma unroll
+          for (int q = 0; q < SHIFT; ++q)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              zacc[KEEP + q][j][0] = zin[q][j][0];
+              zacc[KEEP + q][j][1] = zin[q][j][1];
+            }
+        } else {
+#pragma unroll
+          for (int r = 0; r < TILES; ++r)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) st2(W0 + 8 * r, j, fast, zacc[r][j][0], zacc[r][j][1]);
         }
       }
-#pragma unroll
-      for (int a = 0; a < MI3; ++a)
-#pragma unroll
-        for (int j = 0; j < NI; ++j) {
-          const int r = r0w + a * 8 + 2 * lr, c = wn * 16 + j * 8 + lq;
-          int q0 = zbase + r;  // even, and q0 + 1 < HP: the pair never straddles the ring seam
-          if (q0 >= HP) q0 -= HP;
-          double2* zp = reinterpret_cast<double2*>(Zs + c * LDZ + q0);
-          double2 zv = *zp;
-          zv.x -= acc[a][j][0];
-          zv.y -= acc[a][j][1];
-          *zp = zv;
-        }
+      buf ^= 1;
     }
-    __syncthreads();    // (4) window updated; Vs is free
-    // ---- advance
-    if (nt_ == 0 && nS_ >= 0) ntask = q2_num_tasks(n, B, (i64)nS_ * NBS);
-    S = nS_;
-    t = nt_;
-    pk = npk;
   }
-  evict(min(hi, n));
-}
-
-template <int B, int NBS, int NWN>
-static size_t q2_smem_bytes() {
-  using G = Q2Geom<B, NBS>;
-  constexpr int KC = 16 * NWN;
-  return (size_t)(KC * (G::HP + 4) + G::BLK + KC * (NBS + 4)) * sizeof(double);
 }
 
 // Work per SM is what bounds the walk (every CTA is a serial chain over all diamond blocks): choose the slab
 // width that minimises ceil(#CTA / #SM) * KC, the columns the busiest SM has to process.
-template <int B, int NBS, int NWN>
-static void q2_consider(Ctx* ctx, i64 k, int force_kc, long long* best_cost, int* best_nwn) {
-  constexpr int KC = 16 * NWN;
+template <int NW>
+static void q2_consider(Ctx* ctx, i64 k, int force_kc, long long* best_cost, int* best_nw) {
+  constexpr int KC = 16 * NW;
   if (force_kc > 0 && force_kc != KC) return;
   const long long nct = (k + KC - 1) / KC;
   const long long cost = ((nct + ctx->num_sms - 1) / ctx->num_sms) * KC;
-  if (*best_nwn == 0 || cost < *best_cost || (cost == *best_cost && NWN > *best_nwn)) {
+  if (*best_nw == 0 || cost < *best_cost || (cost == *best_cost && NW > *best_nw)) {
     *best_cost = cost;
-    *best_nwn = NWN;
+    *best_nw = NW;
   }
 }
 
-template <int B, int NBS, int NWN>
+template <int B, int NBS, int NW, bool AL16>
 static cudaError_t q2_apply_launch(Ctx* ctx, const double* packed, const i64* d_off, i64 n, int nS, double* Z, i64 ldz,
                                    i64 k) {
-  const size_t smem = q2_smem_bytes<B, NBS, NWN>();
-  auto kern = q2_apply_kernel<B, NBS, NWN>;
+  using G = Q2Geom<B, NBS>;
+  const size_t smem = (size_t)2 * G::IMG * sizeof(double);
+  auto kern = q2_apply_kernel<B, NBS, NW, AL16>;
   cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (ce != cudaSuccess) return ce;
-  kern<<<cdiv(k, 16 * NWN), 64 * NWN, smem, ctx->stream>>>(packed, d_off, n, nS, Z, ldz, k);
+  kern<<<cdiv(k, 16 * NW), 32 * NW, smem, ctx->stream>>>(packed, d_off, n, nS, Z, ldz, k);
   EKB_COUNT_LAUNCH(ctx);
   return cudaGetLastError();
 }
@@ -424,7 +404,7 @@ static int q2_launch(Ctx* ctx, i64 n, const double* V2, i64 ldv, const double* T
   i64* d_off = nullptr;
   double* packed = nullptr;
   EKB_TRY(ctx_alloc(ctx, (void**)&d_off, (size_t)(nS + 1) * sizeof(i64)));
-  int rc = ctx_alloc(ctx, (void**)&packed, (size_t)nblk * G::BLK * sizeof(double));
+  int rc = ctx_alloc(ctx, (void**)&packed, (size_t)nblk * G::IMG * sizeof(double));
   if (rc) { ctx_free(ctx, d_off); return rc; }
   auto cleanup = [&]() { cudaStreamSynchronize(ctx->stream); ctx_free(ctx, d_off); ctx_free(ctx, packed); };
   cudaError_t ce = cudaMemcpyAsync(d_off, off.data(), (size_t)(nS + 1) * sizeof(i64), cudaMemcpyHostToDevice, ctx->stream);
@@ -436,12 +416,21 @@ static int q2_launch(Ctx* ctx, i64 n, const double* V2, i64 ldv, const double* T
   }
   if (ce == cudaSuccess) {
     long long cost = 0;
-    int nwn = 0;
-    q2_consider<B, NBS, 2>(ctx, k, ctx->q2_kc, &cost, &nwn);
-    q2_consider<B, NBS, 3>(ctx, k, ctx->q2_kc, &cost, &nwn);
-    switch (nwn) {
-      case 2: ce = q2_apply_launch<B, NBS, 2>(ctx, packed, d_off, n, nS, Z, ldz, k); break;
-      case 3: ce = q2_apply_launch<B, NBS, 3>(ctx, packed, d_off, n, nS, Z, ldz, k); break;
+    int nw = 0;
+    q2_consider<4>(ctx, k, ctx->q2_kc, &cost, &nw);
+    q2_consider<5>(ctx, k, ctx->q2_kc, &cost, &nw);
+    q2_consider<6>(ctx, k, ctx->q2_kc, &cost, &nw);
+    q2_consider<7>(ctx, k, ctx->q2_kc, &cost, &nw);
+    q2_consider<8>(ctx, k, ctx->q2_kc, &cost, &nw);
+    const bool al16 = ((uintptr_t)Z & 15) == 0 && (ldz & 1) == 0;
+    if (!al16) nw = -4;  // 8-byte global accesses: one generic instantiation
+    switch (nw) {
+      case -4: ce = q2_apply_launch<B, NBS, 4, false>(ctx, packed, d_off, n, nS, Z, ldz, k); break;
+      case 4: ce = q2_apply_launch<B, NBS, 4, true>(ctx, packed, d_off, n, nS, Z, ldz, k); break;
+      case 5: ce = q2_apply_launch<B, NBS, 5, true>(ctx, packed, d_off, n, nS, Z, ldz, k); break;
+      case 6: ce = q2_apply_launch<B, NBS, 6, true>(ctx, packed, d_off, n, nS, Z, ldz, k); break;
+      case 7: ce = q2_apply_launch<B, NBS, 7, true>(ctx, packed, d_off, n, nS, Z, ldz, k); break;
+      case 8: ce = q2_apply_launch<B, NBS, 8, true>(ctx, packed, d_off, n, nS, Z, ldz, k); break;
       default: ce = cudaErrorInvalidValue;
     }
   }
