@@ -71,9 +71,16 @@ _SIGS = {
     "ekb200_timer_stop": [c_void_p, POINTER(c_double)],
     "ekb200_gemm_profile": [c_void_p, POINTER(c_double), POINTER(c_double), POINTER(c_int64)],
     "ekb200_measure_fp64_peak": [c_void_p, POINTER(c_double), POINTER(c_double)],
+    "ekb200_comm_unique_id": [c_void_p],
+    "ekb200_comm_init": [c_void_p, c_int, c_int, c_void_p],
+    "ekb200_comm_info": [c_void_p, POINTER(c_int), POINTER(c_int)],
+    "ekb200_comm_slab": [c_void_p, c_int64, POINTER(c_int64), POINTER(c_int64)],
+    "ekb200_comm_allgather_slabs": [c_void_p, c_int64, c_int64, c_void_p, c_int64],
+    "ekb200_comm_bcast": [c_void_p, c_void_p, c_int64, c_int],
+    "ekb200_num_collectives": [c_void_p],
 }
 _RESTYPE = {"ekb200_strerror": c_char_p, "ekb200_last_error": c_char_p, "ekb200_last_merge_flops": c_double,
-            "ekb200_num_launches": c_int64}
+            "ekb200_num_launches": c_int64, "ekb200_num_collectives": c_int64}
 
 
 def exported_symbols():

@@ -63,6 +63,7 @@ int ekb200_destroy(ekb200_ctx* h) {
   Ctx* ctx = &h->c;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  comm_destroy(ctx);
   for (void* p : ctx->allocs) cudaFree(p);
   ctx->allocs.clear();
   for (cudaEvent_t ev : ctx->prof_events) cudaEventDestroy(ev);
@@ -81,6 +82,7 @@ const char* ekb200_strerror(int info) {
   if (info == EKB_ERR_CUDA) return "CUDA runtime failure";
   if (info == EKB_ERR_NOMEM) return "device memory allocation failed";
   if (info == EKB_ERR_INTERNAL) return "internal error";
+  if (info == EKB_ERR_COMM) return "NCCL failure";
   return "numerical failure";
 }
 
@@ -237,7 +239,7 @@ int ekb200_sygst(ekb200_ctx* h, int64_t n, double* A, int64_t lda, const double*
   if (n == 0) return 0;
   EKB_TRY(ensure_invd(h, n));
   EKB_TRY(trtri_diag_blocks(ctx, n, L, ldl, h->invd));
-  EKB_TRY(sygst_lower(ctx, n, A, lda, L, ldl, h->invd));
+  EKB_TRY(sygst_dist(ctx, n, A, lda, L, ldl, h->invd));
   EKB_CUDA(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
@@ -300,7 +302,7 @@ int ekb200_stedc(ekb200_ctx* h, int64_t n, double* d, double* e, double* w, doub
   if (n == 0) return 0;
   void* work = nullptr;
   EKB_TRY(ctx_alloc(ctx, &work, stedc_workspace_bytes(n)));
-  int rc = stedc(ctx, n, d, e, w, Z, ldz, work, merge_flops);
+  int rc = stedc(ctx, n, d, e, w, Z, ldz, work, merge_flops, 0, n);
   cudaError_t ce = cudaStreamSynchronize(ctx->stream);
   ctx_free(ctx, work);
   if (rc == 0) EKB_CUDA(ce);
@@ -472,9 +474,14 @@ static int solve_host(ekb200_ctx* h, int64_t n, int64_t nev, const double* A, in
   }
   if (!rc) {
     StageTimer t(ctx, hasB ? "solve_with_general_b200:d2h" : "eigen_solver_b200:d2h");
+    // multi-rank: every rank returns all of w and ITS column slab of the eigenvectors; the caller's Z is then
+    // the LOCAL piece (n x nloc, ekb200_comm_slab), like blacs%Vectors(lld, loc_cols) of the reference
+    std::vector<i64> zb;
+    slab_bounds(nev, ctx->nranks, 128, zb);
+    const i64 c0 = zb[ctx->rank], kc = zb[ctx->rank + 1] - zb[ctx->rank];
     cudaError_t ce = cudaMemcpyAsync(w, dw, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream);
-    if (ce == cudaSuccess)
-      ce = cudaMemcpy2DAsync(Z, ldz * 8, dZ, ld * 8, n * 8, nev, cudaMemcpyDeviceToHost, ctx->stream);
+    if (ce == cudaSuccess && kc > 0)
+      ce = cudaMemcpy2DAsync(Z, ldz * 8, dZ + c0 * ld, ld * 8, n * 8, kc, cudaMemcpyDeviceToHost, ctx->stream);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
     t.stop();
     if (ce != cudaSuccess) {
@@ -530,6 +537,55 @@ int ekb200_sygvd_coo(ekb200_ctx* h, int64_t n, int64_t nev, int64_t nnzA, const 
   CooIn a{nnzA, ijA, vA}, b{nnzB, ijB, vB};
   return solve_host(h, n, nev, nullptr, 0, &a, nnzB > 0, nullptr, 0, nnzB > 0 ? &b : nullptr, w, Z, ldz);
 }
+
+// ---- multi-GPU: one context per rank (dist.cu)
+int ekb200_comm_unique_id(void* id128) {
+  if (!id128) return -1;
+  std::string err;
+  return comm_unique_id(id128, &err);
+}
+int ekb200_comm_init(ekb200_ctx* h, int nranks, int rank, const void* id128) {
+  CHECK_CTX(h);
+  if (nranks < 1) return -2;
+  if (rank < 0 || rank >= nranks) return -3;
+  if (nranks > 1 && !id128) return -4;
+  return comm_init(ctx, nranks, rank, id128);
+}
+int ekb200_comm_info(const ekb200_ctx* h, int* nranks, int* rank) {
+  if (!h) return -1;
+  if (nranks) *nranks = h->c.nranks;
+  if (rank) *rank = h->c.rank;
+  return 0;
+}
+int ekb200_comm_slab(const ekb200_ctx* h, int64_t ncols, int64_t* col0, int64_t* nloc) {
+  if (!h) return -1;
+  if (ncols < 0) return -2;
+  std::vector<i64> zb;
+  slab_bounds(ncols, h->c.nranks, 128, zb);
+  if (col0) *col0 = zb[h->c.rank];
+  if (nloc) *nloc = zb[h->c.rank + 1] - zb[h->c.rank];
+  return 0;
+}
+int ekb200_comm_allgather_slabs(ekb200_ctx* h, int64_t nrows, int64_t ncols, double* M, int64_t ld) {
+  CHECK_CTX(h);
+  if (nrows < 0) return -2;
+  if (ncols < 0) return -3;
+  if (ld < nrows) return -5;
+  std::vector<i64> zb;
+  slab_bounds(ncols, ctx->nranks, 128, zb);
+  EKB_TRY(comm_allgather_cols(ctx, M, ld, zb));
+  EKB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int ekb200_comm_bcast(ekb200_ctx* h, void* dev_buf, int64_t bytes, int root) {
+  CHECK_CTX(h);
+  if (bytes < 0) return -3;
+  if (root < 0 || root >= ctx->nranks) return -4;
+  EKB_TRY(comm_bcast(ctx, dev_buf, (size_t)bytes, root));
+  EKB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int64_t ekb200_num_collectives(const ekb200_ctx* h) { return h ? h->c.collectives : 0; }
 
 int ekb200_measure_fp64_peak(ekb200_ctx* h, double* dmma_tflops, double* dfma_tflops) {
   CHECK_CTX(h);

@@ -5,8 +5,11 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 #include <string>
 #include <vector>
+
+#include "layout.h"
 
 namespace ekb {
 
@@ -14,7 +17,7 @@ typedef long long i64;
 
 // LAPACK-style info codes of the C-ABI: 0 ok, <0 argument -i illegal, >0 numerical failure.
 // Internal CUDA failures map to EKB_ERR_CUDA.
-enum { EKB_ERR_CUDA = 1000001, EKB_ERR_NOMEM = 1000002, EKB_ERR_INTERNAL = 1000003 };
+enum { EKB_ERR_CUDA = 1000001, EKB_ERR_NOMEM = 1000002, EKB_ERR_INTERNAL = 1000003, EKB_ERR_COMM = 1000004 };
 
 struct Event {
   std::string name;
@@ -47,6 +50,10 @@ struct Ctx {
   std::vector<cudaEvent_t> prof_events;   // pairs (start, stop), one per profiled launch
   std::vector<double> prof_flops;         // 2 m n k of that launch
   size_t prof_used = 0;
+  // multi-GPU (dist.cu): one context per rank, NCCL communicator bound at run time
+  int nranks = 1, rank = 0;
+  void* comm = nullptr;               // ncclComm_t
+  long long collectives = 0;          // NCCL collectives issued by this context
 };
 #define EKB_COUNT_LAUNCH(c) ((c)->launches++)
 
@@ -142,6 +149,19 @@ int sygvd_dev(Ctx* ctx, i64 n, i64 nev, double* A, i64 lda, double* B, i64 ldb, 
               double* invd, double* merge_flops);
 
 size_t stedc_workspace_bytes(i64 n);
-int stedc(Ctx* ctx, i64 n, double* d, double* e, double* w, double* Z, i64 ldz, void* work, double* flops_out);
+// Only the eigenvector columns [col_lo, col_hi) (ascending-eigenvalue positions) of the TOP merge are formed
+// (all of them for col_lo = 0, col_hi = n); the other columns of Z are left undefined.
+int stedc(Ctx* ctx, i64 n, double* d, double* e, double* w, double* Z, i64 ldz, void* work, double* flops_out,
+          i64 col_lo, i64 col_hi);
+
+// ---------------------------------------------------------------- multi-GPU (dist.cu)
+int comm_unique_id(void* id128, std::string* err);
+int comm_init(Ctx* ctx, int nranks, int rank, const void* id128);
+int comm_destroy(Ctx* ctx);
+int comm_allgather_cols(Ctx* ctx, double* M, i64 ld, const std::vector<i64>& bounds);
+int comm_bcast(Ctx* ctx, void* buf, size_t bytes, int root);
+int comm_allgather(Ctx* ctx, const double* send, double* recv, size_t count);
+int transpose_matrix(Ctx* ctx, const double* A, i64 lda, i64 m, i64 n, double* B, i64 ldb);
+int sygst_dist(Ctx* ctx, i64 n, double* A, i64 lda, const double* L, i64 ldl, const double* invd);
 
 }  // namespace ekb

@@ -38,9 +38,17 @@ struct Scratch {
 }  // namespace
 
 // A (n x n, full symmetric, destroyed) -> w (n, ascending), Z (n x nev: eigenvectors of the nev lowest).
+// With P > 1 ranks (dist.cu) every rank enters with the same A and leaves with all of w and with ITS column
+// slab Z(:, c0 : c0+kc) (slab_bounds(nev, P, 128)); the other columns of Z are scratch.  Dense-to-band is
+// sharded by block columns, bulge chasing and the lower D&C levels are replicated, the top D&C merge and
+// both back-transformations act on the slab only (no data-path collective).
 int syevd_dev(Ctx* ctx, i64 n, i64 nev, double* A, i64 lda, double* w, double* Z, i64 ldz, double* merge_flops) {
   if (n <= 0 || nev <= 0) return 0;
   const int b = ctx->band;
+  std::vector<i64> zb;
+  slab_bounds(nev, ctx->nranks, 128, zb);
+  const i64 c0 = zb[ctx->rank], kc = zb[ctx->rank + 1] - zb[ctx->rank];
+  double* Zs = Z + c0 * ldz;  // this rank's slab
   Scratch sc(ctx);
   StageTimer total(ctx, "eigen_solver_b200");
   const i64 ldab = 2 * b;
@@ -81,13 +89,13 @@ int syevd_dev(Ctx* ctx, i64 n, i64 nev, double* A, i64 lda, double* w, double* Z
     EKB_TRY(sc.get(&work, stedc_workspace_bytes(n)));
     int rc;
     if (nev == n) {
-      rc = stedc(ctx, n, d, e, w, Z, ldz, work, merge_flops);
+      rc = stedc(ctx, n, d, e, w, Z, ldz, work, merge_flops, c0, c0 + kc);
     } else {
       double* ZT = nullptr;
       const i64 ldt = round_up(n, 8);
       EKB_TRY(sc.get((void**)&ZT, (size_t)ldt * n * sizeof(double)));
-      rc = stedc(ctx, n, d, e, w, ZT, ldt, work, merge_flops);
-      if (rc == 0) rc = copy_matrix(ctx, ZT, ldt, Z, ldz, n, nev);
+      rc = stedc(ctx, n, d, e, w, ZT, ldt, work, merge_flops, c0, c0 + kc);
+      if (rc == 0) rc = copy_matrix(ctx, ZT + c0 * ldt, ldt, Zs, ldz, n, kc);
       sc.release(ZT);
     }
     t.stop();
@@ -96,7 +104,7 @@ int syevd_dev(Ctx* ctx, i64 n, i64 nev, double* A, i64 lda, double* w, double* Z
   }
   {
     StageTimer t(ctx, "eigen_solver_b200:ormtr_sb2st");
-    int rc = apply_q2(ctx, n, b, V2, ldv, TAU2, ldtau, nev, Z, ldz);
+    int rc = kc > 0 ? apply_q2(ctx, n, b, V2, ldv, TAU2, ldtau, kc, Zs, ldz) : 0;
     t.stop();
     if (rc) return rc;
   }
@@ -105,8 +113,8 @@ int syevd_dev(Ctx* ctx, i64 n, i64 nev, double* A, i64 lda, double* w, double* Z
   {
     StageTimer t(ctx, "eigen_solver_b200:ormtr_sy2sb");
     double* work = nullptr;
-    EKB_TRY(sc.get((void**)&work, apply_q1_workspace_doubles(n, b, nev) * sizeof(double)));
-    int rc = apply_q1(ctx, n, b, A, lda, T1, nev, Z, ldz, work);
+    EKB_TRY(sc.get((void**)&work, apply_q1_workspace_doubles(n, b, kc > 0 ? kc : 1) * sizeof(double)));
+    int rc = kc > 0 ? apply_q1(ctx, n, b, A, lda, T1, kc, Zs, ldz, work) : 0;
     t.stop();
     sc.release(work);
     if (rc) return rc;
@@ -131,7 +139,7 @@ int sygvd_dev(Ctx* ctx, i64 n, i64 nev, double* A, i64 lda, double* B, i64 ldb, 
     }
     {
       StageTimer t(ctx, "reduce_generalized_b200:sygst");
-      int rc = sygst_lower(ctx, n, A, lda, B, ldb, invd);
+      int rc = sygst_dist(ctx, n, A, lda, B, ldb, invd);
       t.stop();
       if (rc) return rc;
     }
@@ -140,7 +148,10 @@ int sygvd_dev(Ctx* ctx, i64 n, i64 nev, double* A, i64 lda, double* B, i64 ldb, 
   EKB_TRY(syevd_dev(ctx, n, nev, A, lda, w, Z, ldz, merge_flops));
   {
     StageTimer t(ctx, "recovery_generalized_b200");
-    int rc = trsm_lower(ctx, TRSM_LLT, n, nev, B, ldb, invd, Z, ldz);
+    std::vector<i64> zb;
+    slab_bounds(nev, ctx->nranks, 128, zb);
+    const i64 c0 = zb[ctx->rank], kc = zb[ctx->rank + 1] - zb[ctx->rank];
+    int rc = kc > 0 ? trsm_lower(ctx, TRSM_LLT, n, kc, B, ldb, invd, Z + c0 * ldz, ldz) : 0;
     t.stop();
     if (rc) return rc;
   }

@@ -377,22 +377,42 @@ __global__ void __launch_bounds__(256) dc_pack_kernel(const DcNode* __restrict__
   if (g >= nd.k1 && r < n2) W1[(i64)(off + g - nd.k1) * ldw + off + n1 + r] = src[n1 + r];
 }
 
+// Root columns [crange[0], crange[1]) of the (single) top node whose sorted position falls in [col_lo, col_hi):
+// the roots are ascending in c, so the wanted ones form one contiguous range (a superset is harmless).
+__global__ void __launch_bounds__(256) dc_colrange_kernel(const DcNode* __restrict__ nodes, DcWork wk, int col_lo, int col_hi,
+                                                          int* __restrict__ crange) {
+  const DcNode nd = nodes[0];
+  __shared__ int smin, smax;
+  if (threadIdx.x == 0) { smin = nd.k; smax = 0; }
+  __syncthreads();
+  for (int c = threadIdx.x; c < nd.k; c += blockDim.x) {
+    const int p = wk.pos[nd.off + c];
+    if (p >= col_lo && p < col_hi) { atomicMin(&smin, c); atomicMax(&smax, c + 1); }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) { crange[0] = smin; crange[1] = smax > smin ? smax : smin; }
+}
+
+// crange != nullptr (top level of a column-restricted solve): only root columns [crange[0], crange[1]).
 __global__ void dc_gemm_setup_kernel(const DcNode* __restrict__ nodes, int nnodes, GemmP* __restrict__ gp, const double* W1,
-                                     i64 ldw, const double* U, i64 ldu, double* W2, i64 ldw2) {
+                                     i64 ldw, const double* U, i64 ldu, double* W2, i64 ldw2,
+                                     const int* __restrict__ crange) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nnodes) return;
   const DcNode nd = nodes[t];
   const i64 off = nd.off;
+  const i64 ca = crange ? crange[0] : 0;
+  const int ncol = crange ? crange[1] - crange[0] : nd.k;
   GemmP a, b;
-  a.m = nd.n1; a.n = nd.k; a.k = nd.k1 + nd.k2;
+  a.m = nd.n1; a.n = ncol; a.k = nd.k1 + nd.k2;
   a.A = W1 + off * ldw + off; a.lda = ldw;
-  a.B = U + off * ldu + off; a.ldb = ldu;
-  a.C = W2 + off * ldw2 + off; a.ldc = ldw2;
+  a.B = U + (off + ca) * ldu + off; a.ldb = ldu;
+  a.C = W2 + (off + ca) * ldw2 + off; a.ldc = ldw2;
   a.alpha = 1.0; a.beta = 0.0;
-  b.m = nd.sz - nd.n1; b.n = nd.k; b.k = nd.k2 + nd.k3;
+  b.m = nd.sz - nd.n1; b.n = ncol; b.k = nd.k2 + nd.k3;
   b.A = W1 + off * ldw + off + nd.n1; b.lda = ldw;
-  b.B = U + off * ldu + off + nd.k1; b.ldb = ldu;
-  b.C = W2 + off * ldw2 + off + nd.n1; b.ldc = ldw2;
+  b.B = U + (off + ca) * ldu + off + nd.k1; b.ldb = ldu;
+  b.C = W2 + (off + ca) * ldw2 + off + nd.n1; b.ldc = ldw2;
   b.alpha = 1.0; b.beta = 0.0;
   gp[2 * t] = a;
   gp[2 * t + 1] = b;
@@ -427,7 +447,7 @@ __global__ void __launch_bounds__(256) dc_rank_kernel(const DcNode* __restrict__
 // Qnew[:, pos[c]] = c < k ? W2[:, c] : Qcur[:, defl_col[c-k]]
 __global__ void __launch_bounds__(256) dc_permute_kernel(const DcNode* __restrict__ nodes, DcWork wk, const double* __restrict__ W2,
                                                          i64 ldw2, const double* __restrict__ Qcur, i64 ldq,
-                                                         double* __restrict__ Qnew, i64 ldn) {
+                                                         double* __restrict__ Qnew, i64 ldn, int col_lo, int col_hi) {
   const DcNode nd = nodes[blockIdx.z];
   const int c = blockIdx.x;
   if (c >= nd.sz) return;
@@ -435,6 +455,7 @@ __global__ void __launch_bounds__(256) dc_permute_kernel(const DcNode* __restric
   const int r = blockIdx.y * blockDim.x + threadIdx.x;
   if (r >= nd.sz) return;
   const int p = wk.pos[off + c];
+  if (p < col_lo || p >= col_hi) return;
   double v;
   if (c < nd.k) v = W2[(i64)(off + c) * ldw2 + off + r];
   else v = Qcur[(i64)(off + wk.defl_col[off + c - nd.k]) * ldq + off + r];
@@ -452,8 +473,13 @@ size_t stedc_workspace_bytes(i64 n) {
 
 // d (n), e (n-1): tridiagonal (destroyed).  w (n): eigenvalues ascending.  Z (n x n, ldz): eigenvectors.
 // work: stedc_workspace_bytes(n) bytes.  flops_out (optional, host): actual merge GEMM FLOPs.
-int stedc(Ctx* ctx, i64 n, double* d, double* e, double* w, double* Z, i64 ldz, void* work, double* flops_out) {
+int stedc(Ctx* ctx, i64 n, double* d, double* e, double* w, double* Z, i64 ldz, void* work, double* flops_out,
+          i64 col_lo, i64 col_hi) {
   if (n <= 0) return 0;
+  if (col_lo < 0) col_lo = 0;
+  if (col_hi > n) col_hi = n;
+  if (col_hi < col_lo) col_hi = col_lo;
+  const bool restricted = (col_lo > 0 || col_hi < n);
   const i64 ld = round_up(n, 8);
   char* wp = (char*)work;
   auto take = [&](size_t bytes) { void* p = wp; wp += (bytes + 255) / 256 * 256; return p; };
@@ -527,12 +553,22 @@ int stedc(Ctx* ctx, i64 n, double* d, double* e, double* w, double* Z, i64 ldz, 
     // U lives in the (not yet written) next-level Q buffer
     dc_buildU_kernel<<<dim3(maxsz, cnt), 128, 0, ctx->stream>>>(nodes, wk, Qnxt, ldnxt); EKB_COUNT_LAUNCH(ctx);
     dc_pack_kernel<<<dim3(maxsz, cdiv(maxn1, 256), cnt), 256, 0, ctx->stream>>>(nodes, wk, Qcur, ldcur, W1, ld); EKB_COUNT_LAUNCH(ctx);
-    dc_gemm_setup_kernel<<<cdiv(cnt, 128), 128, 0, ctx->stream>>>(nodes, cnt, d_gp, W1, ld, Qnxt, ldnxt, W2, ld); EKB_COUNT_LAUNCH(ctx);
-    EKB_CUDA(cudaGetLastError());
-    EKB_TRY(gemm_batched(ctx, 0, d_gp, 2 * cnt, maxn1, maxsz));
+    // final positions of the merged spectrum (independent of the products, so it can steer them)
     dc_rank_kernel<<<dim3(cdiv(maxsz, 256), cnt), 256, 0, ctx->stream>>>(nodes, wk, Dnxt); EKB_COUNT_LAUNCH(ctx);
+    const bool top_cut = restricted && l == 0;  // only the caller's eigenvector columns of the top merge
+    int* crange = nullptr;
+    int plo = 0, phi = 0x7fffffff, max_cols = maxsz;
+    if (top_cut) {
+      crange = ctx->d_info + 8;
+      plo = (int)col_lo; phi = (int)col_hi;
+      max_cols = (int)std::max<i64>(1, col_hi - col_lo);
+      dc_colrange_kernel<<<1, 256, 0, ctx->stream>>>(nodes, wk, plo, phi, crange); EKB_COUNT_LAUNCH(ctx);
+    }
+    dc_gemm_setup_kernel<<<cdiv(cnt, 128), 128, 0, ctx->stream>>>(nodes, cnt, d_gp, W1, ld, Qnxt, ldnxt, W2, ld, crange); EKB_COUNT_LAUNCH(ctx);
+    EKB_CUDA(cudaGetLastError());
+    if (col_hi > col_lo || !top_cut) EKB_TRY(gemm_batched(ctx, 0, d_gp, 2 * cnt, maxn1, max_cols));
     dc_permute_kernel<<<dim3(maxsz, cdiv(maxsz, 256), cnt), 256, 0, ctx->stream>>>(nodes, wk, W2, ld, Qcur, ldcur, Qnxt,
-                                                                                ldnxt); EKB_COUNT_LAUNCH(ctx);
+                                                                                ldnxt, plo, phi); EKB_COUNT_LAUNCH(ctx);
     EKB_CUDA(cudaGetLastError());
     std::swap(Qcur, Qnxt);
     std::swap(ldcur, ldnxt);
@@ -542,13 +578,19 @@ int stedc(Ctx* ctx, i64 n, double* d, double* e, double* w, double* Z, i64 ldz, 
   if (Qcur != Z || Dcur != w) return EKB_ERR_INTERNAL;
   // failure flag + actual FLOP count
   EKB_CUDA(cudaMemcpyAsync(ctx->h_info + 1, ctx->d_info + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  if (restricted)
+    EKB_CUDA(cudaMemcpyAsync(ctx->h_info + 8, ctx->d_info + 8, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   if (flops_out && !hn.empty())
     EKB_CUDA(cudaMemcpyAsync(hn.data(), d_nodes, hn.size() * sizeof(DcNode), cudaMemcpyDeviceToHost, ctx->stream));
   EKB_CUDA(cudaStreamSynchronize(ctx->stream));
   if (flops_out) {
     double fl = 0.0;
-    for (const DcNode& nd : hn)
-      fl += 2.0 * nd.k * ((double)nd.n1 * (nd.k1 + nd.k2) + (double)(nd.sz - nd.n1) * (nd.k2 + nd.k3));
+    for (size_t q = 0; q < hn.size(); ++q) {
+      const DcNode& nd = hn[q];
+      double cols = nd.k;
+      if (restricted && (int)q == lvl_start[0]) cols = ctx->h_info[9] - ctx->h_info[8];
+      fl += 2.0 * cols * ((double)nd.n1 * (nd.k1 + nd.k2) + (double)(nd.sz - nd.n1) * (nd.k2 + nd.k3));
+    }
     *flops_out = fl;
   }
   if (ctx->h_info[1] != 0) return ctx->h_info[1];  // number of leaves whose QL iteration failed

@@ -146,6 +146,27 @@ int ekb200_timer_start(ekb200_ctx* ctx);
 int ekb200_timer_stop(ekb200_ctx* ctx, double* seconds);
 int ekb200_gemm_profile(ekb200_ctx* ctx, double* seconds, double* flops, int64_t* launches);
 
+/* ---- multi-GPU: ONE CONTEXT PER RANK, one rank per B200 (replaces the BLACS grid of src/processes.f90:17-65 and
+ * the block-cyclic scatter of src/distribute_matrix.f90:92-148).  Rank 0 obtains a 128-byte id with
+ * ekb200_comm_unique_id and hands it to the other ranks by whatever the host has (mpi_bcast in the Fortran app,
+ * torch.distributed in the Python mirror); every rank then calls ekb200_comm_init.  After that the SAME solve entry
+ * points run sharded: every rank passes the same (replicated) A and B -- exactly like the replicated COO the reference
+ * hands to solve_with_general_scalapack (solver_scalapack_all.f90:127-132) -- and receives all of w and ITS column
+ * slab of the eigenvectors, columns [col0, col0 + nloc) from ekb200_comm_slab(nev): a 1 x P process grid with one
+ * column block per rank.  Host-pointer entry points: Z is the LOCAL piece (n x nloc, ldz), the analogue of
+ * blacs%Vectors(lld, loc_cols); *_dev entry points: dev_Z is the full n x nev buffer on every rank (scratch outside
+ * the slab), of which columns [col0, col0 + nloc) hold the result.  NCCL (bound with dlopen) carries
+ * the all-gathers of the sharded pdsygst and the panel exchanges of the sharded dense-to-band reduction; the
+ * back-transformations, the top D&C merge and pdtrtrs work on the slab with no data-path collective. */
+int ekb200_comm_unique_id(void* id128);
+int ekb200_comm_init(ekb200_ctx* ctx, int nranks, int rank, const void* id128);
+int ekb200_comm_info(const ekb200_ctx* ctx, int* nranks, int* rank);
+int ekb200_comm_slab(const ekb200_ctx* ctx, int64_t ncols, int64_t* col0, int64_t* nloc);
+/* every rank owns its slab of the columns of dev_M (nrows x ncols, ld): afterwards all ranks hold all columns */
+int ekb200_comm_allgather_slabs(ekb200_ctx* ctx, int64_t nrows, int64_t ncols, double* dev_M, int64_t ld);
+int ekb200_comm_bcast(ekb200_ctx* ctx, void* dev_buf, int64_t bytes, int root);
+int64_t ekb200_num_collectives(const ekb200_ctx* ctx);
+
 /* ---- measurement helper (roofline denominator; never on the solve path) */
 int ekb200_measure_fp64_peak(ekb200_ctx* ctx, double* dmma_tflops, double* dfma_tflops);
 
