@@ -229,9 +229,21 @@ def run_ours(args) -> None:
     launches = lib.ekb200_num_launches(h) - launches0
     collectives = lib.ekb200_num_collectives(h)
     clocks = sampler.stop() if rank == 0 else {}
-    gs, gf, gl = ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
-    ctx.call("ekb200_gemm_profile", ctypes.byref(gs), ctypes.byref(gf), ctypes.byref(gl))
+    NF = 8
+    fam_s, fam_w, fam_l = (ctypes.c_double * NF)(), (ctypes.c_double * NF)(), (ctypes.c_int64 * NF)()
+    ctx.call("ekb200_kernel_profile", fam_s, fam_w, fam_l)
     ctx.set_option("profile_gemm", 0)
+    gs, gf, gl = ctypes.c_double(fam_s[0]), ctypes.c_double(fam_w[0]), ctypes.c_int64(fam_l[0])
+    FAM = ["gemm_engine", "panel_qr", "q2_apply", "sb2st", "gemm_batched", "nccl"]
+    prof_rows = {}
+    for i in range(lib.ekb200_profile_rows(h)):
+        st, fm, ps, pw, pl = ctypes.c_char_p(), ctypes.c_int(), ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
+        lib.ekb200_profile_row(h, i, ctypes.byref(st), ctypes.byref(fm), ctypes.byref(ps), ctypes.byref(pw),
+                               ctypes.byref(pl))
+        ent = {"seconds": ps.value / K, "launches": pl.value // K}
+        if pw.value > 0 and ps.value > 0:
+            ent["tflops_or_tbs"] = pw.value / ps.value / 1e12
+        prof_rows.setdefault(st.value.decode(), {})[FAM[fm.value] if fm.value < len(FAM) else str(fm.value)] = ent
     stage = {name: s / K for name, s, rep in ctx.events()}
     merge_flops = lib.ekb200_last_merge_flops(h)
     seconds = max(sec.value, 0.0)
@@ -350,7 +362,7 @@ def run_ours(args) -> None:
         "seconds_per_solve": seconds / K, "wall_seconds_per_solve": wall / K,
         "clocks": clocks, "e2e": e2e if e2e is not None else ({"skipped": e2e_skip} if e2e_skip else None),
         "gpu_launches": int(launches), "nccl_collectives": int(collectives), "roofline": roof, "stages": stages,
-        "fp64_peak_measured": peak, "cpu_baseline": cpu,
+        "kernel_profile": prof_rows, "fp64_peak_measured": peak, "cpu_baseline": cpu,
     }
     print(json.dumps(line))
     ctx.close()

@@ -71,6 +71,10 @@ _SIGS = {
     "ekb200_timer_stop": [c_void_p, POINTER(c_double)],
     "ekb200_gemm_profile": [c_void_p, POINTER(c_double), POINTER(c_double), POINTER(c_int64)],
     "ekb200_measure_fp64_peak": [c_void_p, POINTER(c_double), POINTER(c_double)],
+    "ekb200_kernel_profile": [c_void_p, POINTER(c_double), POINTER(c_double), POINTER(c_int64)],
+    "ekb200_profile_rows": [c_void_p],
+    "ekb200_profile_row": [c_void_p, c_int, POINTER(c_char_p), POINTER(c_int), POINTER(c_double), POINTER(c_double),
+                           POINTER(c_int64)],
     "ekb200_comm_unique_id": [c_void_p],
     "ekb200_comm_init": [c_void_p, c_int, c_int, c_void_p],
     "ekb200_comm_info": [c_void_p, POINTER(c_int), POINTER(c_int)],

@@ -105,6 +105,8 @@ int ekb200_set_option(ekb200_ctx* h, const char* key, int64_t value) {
     ctx->profile_gemm = value != 0;
     ctx->prof_used = 0;
     ctx->prof_flops.clear();
+    ctx->prof_family.clear();
+    ctx->prof_stage.clear();
     return 0;
   }
   return -2;
@@ -412,6 +414,29 @@ int ekb200_gemm_profile(ekb200_ctx* h, double* seconds, double* flops, int64_t* 
   int rc = gemm_profile_collect(ctx, seconds, flops, &l);
   *launches = l;
   return rc;
+}
+int ekb200_kernel_profile(ekb200_ctx* h, double* seconds, double* work, int64_t* launches) {
+  CHECK_CTX(h);
+  if (!seconds) return -2;
+  if (!work) return -3;
+  if (!launches) return -4;
+  long long l[PROF_FAMILIES];
+  int rc = profile_collect(ctx, seconds, work, l);
+  for (int f = 0; f < PROF_FAMILIES; ++f) launches[f] = l[f];
+  return rc;
+}
+int ekb200_profile_rows(const ekb200_ctx* h) { return h ? (int)h->c.prof_table.size() : 0; }
+int ekb200_profile_row(const ekb200_ctx* h, int i, const char** stage, int* family, double* seconds, double* work,
+                       int64_t* launches) {
+  if (!h) return -1;
+  if (i < 0 || i >= (int)h->c.prof_table.size()) return -2;
+  const Ctx::ProfRow& r = h->c.prof_table[i];
+  if (stage) *stage = r.stage.c_str();
+  if (family) *family = r.family;
+  if (seconds) *seconds = r.seconds;
+  if (work) *work = r.work;
+  if (launches) *launches = r.launches;
+  return 0;
 }
 int64_t ekb200_num_launches(const ekb200_ctx* h) { return h ? h->c.launches : 0; }
 

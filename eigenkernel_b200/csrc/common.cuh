@@ -48,8 +48,13 @@ struct Ctx {
   long long launches = 0;             // kernels launched by this context (bench.py: gpu_launches)
   bool profile_gemm = false;          // per-launch CUDA events around every engine GEMM (roofline evidence)
   std::vector<cudaEvent_t> prof_events;   // pairs (start, stop), one per profiled launch
-  std::vector<double> prof_flops;         // 2 m n k of that launch
+  std::vector<double> prof_flops;         // algorithmic work of that launch (FLOPs, or bytes for HBM-bound families)
+  std::vector<int> prof_family;           // kernel family of that launch (ProfFamily)
+  std::vector<const char*> prof_stage;    // innermost StageTimer name active at that launch
+  const char* cur_stage = "";
   size_t prof_used = 0;
+  struct ProfRow { std::string stage; int family; double seconds, work; long long launches; };
+  std::vector<ProfRow> prof_table;        // (stage, family) aggregation of the last profile_collect
   // multi-GPU (dist.cu): one context per rank, NCCL communicator bound at run time
   int nranks = 1, rank = 0;
   void* comm = nullptr;               // ncclComm_t
@@ -82,6 +87,7 @@ struct StageTimer {
   Ctx* ctx;
   const char* name;
   cudaEvent_t a, b;
+  const char* prev_stage;
   bool done = false;
   StageTimer(Ctx* c, const char* n);
   ~StageTimer();  // a timer abandoned by an early error return records nothing
@@ -112,6 +118,13 @@ int gemm(Ctx* ctx, int flags, const GemmP& p, int tri_keep = -1, int splitk = 1)
 // Batched: `batch` is a DEVICE array of nb problems; (max_m, max_n) bound the grid.
 int gemm_batched(Ctx* ctx, int flags, const GemmP* d_batch, int nb, int max_m, int max_n);
 int gemm_profile_collect(Ctx* ctx, double* seconds, double* flops, long long* launches);
+// Per-launch CUDA-event brackets in "profile_gemm" mode, tagged by kernel family (roofline evidence measured
+// live inside bench.py).  prof_begin/prof_end are no-ops when profiling is off.
+enum ProfFamily { PROF_GEMM = 0, PROF_PANEL_QR = 1, PROF_Q2_APPLY = 2, PROF_SB2ST = 3, PROF_GEMM_BATCHED = 4,
+                  PROF_NCCL = 5, PROF_FAMILIES = 8 };
+int prof_begin(Ctx* ctx, int family, double work);
+int prof_end(Ctx* ctx);
+int profile_collect(Ctx* ctx, double* seconds /*[PROF_FAMILIES]*/, double* work, long long* launches);
 
 // ---------------------------------------------------------------- elementwise helpers (fill.cu)
 int fill_synthetic(Ctx* ctx, double* A, i64 lda, i64 n, uint64_t seed, double offdiag_scale, int diag_mode,
@@ -161,6 +174,8 @@ int comm_destroy(Ctx* ctx);
 int comm_allgather_cols(Ctx* ctx, double* M, i64 ld, const std::vector<i64>& bounds);
 int comm_bcast(Ctx* ctx, void* buf, size_t bytes, int root);
 int comm_allgather(Ctx* ctx, const double* send, double* recv, size_t count);
+int comm_allreduce_sum(Ctx* ctx, double* buf, size_t count);
+int sy2sb_dist(Ctx* ctx, i64 n, int b, double* A, i64 lda, double* AB, i64 ldab, double* T1);
 int transpose_matrix(Ctx* ctx, const double* A, i64 lda, i64 m, i64 n, double* B, i64 ldb);
 int sygst_dist(Ctx* ctx, i64 n, double* A, i64 lda, const double* L, i64 ldl, const double* invd);
 

@@ -40,12 +40,15 @@ void ctx_add_event(Ctx* ctx, const char* name, double seconds) {
 }
 
 StageTimer::StageTimer(Ctx* c, const char* n) : ctx(c), name(n) {
+  prev_stage = ctx->cur_stage;
+  ctx->cur_stage = n;
   cudaEventCreate(&a);
   cudaEventCreate(&b);
   cudaEventRecord(a, ctx->stream);
 }
 StageTimer::~StageTimer() {
   if (!done) {
+    ctx->cur_stage = prev_stage;
     cudaEventDestroy(a);
     cudaEventDestroy(b);
   }
@@ -53,6 +56,7 @@ StageTimer::~StageTimer() {
 double StageTimer::stop() {
   if (done) return 0.0;
   done = true;
+  ctx->cur_stage = prev_stage;
   cudaEventRecord(b, ctx->stream);
   cudaEventSynchronize(b);
   float ms = 0.f;

@@ -29,6 +29,7 @@ struct NcclApi {
   int (*CommDestroy)(NcclComm) = nullptr;
   int (*Broadcast)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
   int (*AllGather)(const void*, void*, size_t, int, NcclComm, cudaStream_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
   int (*GroupStart)() = nullptr;
   int (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
@@ -62,6 +63,7 @@ static int nccl_load() {
   BIND(CommDestroy, "ncclCommDestroy");
   BIND(Broadcast, "ncclBroadcast");
   BIND(AllGather, "ncclAllGather");
+  BIND(AllReduce, "ncclAllReduce");
   BIND(GroupStart, "ncclGroupStart");
   BIND(GroupEnd, "ncclGroupEnd");
   BIND(GetErrorString, "ncclGetErrorString");
@@ -132,6 +134,7 @@ int comm_destroy(Ctx* ctx) {
 // afterwards every rank holds all of them.  One grouped set of broadcasts (slabs may be uneven).
 int comm_allgather_cols(Ctx* ctx, double* M, i64 ld, const std::vector<i64>& bounds) {
   if (ctx->nranks <= 1) return 0;
+  EKB_TRY(prof_begin(ctx, PROF_NCCL, 8.0 * (double)ld * (double)(bounds[ctx->nranks] - bounds[0])));
   EKB_NCCL(g_nccl.GroupStart());
   for (int r = 0; r < ctx->nranks; ++r) {
     const i64 c0 = bounds[r], nc = bounds[r + 1] - bounds[r];
@@ -141,13 +144,26 @@ int comm_allgather_cols(Ctx* ctx, double* M, i64 ld, const std::vector<i64>& bou
   }
   EKB_NCCL(g_nccl.GroupEnd());
   ctx->collectives++;
+  EKB_TRY(prof_end(ctx));
   return 0;
 }
 
 int comm_bcast(Ctx* ctx, void* buf, size_t bytes, int root) {
   if (ctx->nranks <= 1 || bytes == 0) return 0;
+  EKB_TRY(prof_begin(ctx, PROF_NCCL, (double)bytes));
   EKB_NCCL(g_nccl.Broadcast(buf, buf, bytes, NCCL_INT8, root, (NcclComm)ctx->comm, ctx->stream));
   ctx->collectives++;
+  EKB_TRY(prof_end(ctx));
+  return 0;
+}
+
+// buf (count doubles) <- sum over ranks, identical bits on every rank
+int comm_allreduce_sum(Ctx* ctx, double* buf, size_t count) {
+  if (ctx->nranks <= 1 || count == 0) return 0;
+  EKB_TRY(prof_begin(ctx, PROF_NCCL, 8.0 * (double)count));
+  EKB_NCCL(g_nccl.AllReduce(buf, buf, count, NCCL_FLOAT64, /*ncclSum*/ 0, (NcclComm)ctx->comm, ctx->stream));
+  ctx->collectives++;
+  EKB_TRY(prof_end(ctx));
   return 0;
 }
 

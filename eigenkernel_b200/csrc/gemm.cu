@@ -264,23 +264,14 @@ int gemm(Ctx* ctx, int flags, const GemmP& p, int tri_keep, int splitk) {
   }
   if (splitk < 1) splitk = 1;
   int rc;
-  const bool prof = ctx->profile_gemm;
-  if (prof) {
-    if (ctx->prof_used + 2 > ctx->prof_events.size()) {
-      for (int q = 0; q < 2048; ++q) {
-        cudaEvent_t ev;
-        EKB_CUDA(cudaEventCreate(&ev));
-        ctx->prof_events.push_back(ev);
-      }
-    }
+  {
     // algorithmic FLOPs: 2 k per computed element; triangular updates count the kept triangle only
     double elems = (double)p.m * p.n;
     if (tri_keep >= 0) {
       const double mn = p.m < p.n ? p.m : p.n;
       elems = (double)p.m * p.n - 0.5 * mn * (mn - 1.0);
     }
-    ctx->prof_flops.push_back(2.0 * p.k * elems);
-    EKB_CUDA(cudaEventRecord(ctx->prof_events[ctx->prof_used], ctx->stream));
+    EKB_TRY(prof_begin(ctx, PROF_GEMM, 2.0 * p.k * elems));
   }
   if (p.n <= 64)
     rc = launch_cfg<128, 64, 32, 32, false>(ctx, flags, p, nullptr, 1, p.m, p.n, tri_keep, splitk);
@@ -296,36 +287,83 @@ int gemm(Ctx* ctx, int flags, const GemmP& p, int tri_keep, int splitk) {
     EKB_COUNT_LAUNCH(ctx);
     EKB_CUDA(cudaGetLastError());
   }
-  if (prof) {
-    EKB_CUDA(cudaEventRecord(ctx->prof_events[ctx->prof_used + 1], ctx->stream));
-    ctx->prof_used += 2;
-  }
+  EKB_TRY(prof_end(ctx));
   return 0;
 }
 
-// Sum of the per-launch device times and algorithmic FLOPs recorded since the last call (profile_gemm mode).
-int gemm_profile_collect(Ctx* ctx, double* seconds, double* flops, long long* launches) {
+int prof_begin(Ctx* ctx, int family, double work) {
+  if (!ctx->profile_gemm) return 0;
+  if (ctx->prof_used + 2 > ctx->prof_events.size()) {
+    for (int q = 0; q < 2048; ++q) {
+      cudaEvent_t ev;
+      EKB_CUDA(cudaEventCreate(&ev));
+      ctx->prof_events.push_back(ev);
+    }
+  }
+  ctx->prof_flops.push_back(work);
+  ctx->prof_family.push_back(family);
+  ctx->prof_stage.push_back(ctx->cur_stage);
+  EKB_CUDA(cudaEventRecord(ctx->prof_events[ctx->prof_used], ctx->stream));
+  return 0;
+}
+
+int prof_end(Ctx* ctx) {
+  if (!ctx->profile_gemm) return 0;
+  EKB_CUDA(cudaEventRecord(ctx->prof_events[ctx->prof_used + 1], ctx->stream));
+  ctx->prof_used += 2;
+  return 0;
+}
+
+int profile_collect(Ctx* ctx, double* seconds, double* work, long long* launches) {
   EKB_CUDA(cudaStreamSynchronize(ctx->stream));
-  double s = 0.0, f = 0.0;
+  for (int f = 0; f < PROF_FAMILIES; ++f) { seconds[f] = 0.0; work[f] = 0.0; launches[f] = 0; }
+  ctx->prof_table.clear();
   for (size_t q = 0; q + 1 < ctx->prof_used; q += 2) {
     float ms = 0.f;
     EKB_CUDA(cudaEventElapsedTime(&ms, ctx->prof_events[q], ctx->prof_events[q + 1]));
-    s += ms * 1e-3;
-    f += ctx->prof_flops[q / 2];
+    const int f = ctx->prof_family[q / 2];
+    seconds[f] += ms * 1e-3;
+    work[f] += ctx->prof_flops[q / 2];
+    launches[f] += 1;
+    const char* st = ctx->prof_stage[q / 2];
+    Ctx::ProfRow* row = nullptr;
+    for (auto& r : ctx->prof_table)
+      if (r.family == f && r.stage == st) { row = &r; break; }
+    if (!row) {
+      ctx->prof_table.push_back(Ctx::ProfRow{st, f, 0.0, 0.0, 0});
+      row = &ctx->prof_table.back();
+    }
+    row->seconds += ms * 1e-3;
+    row->work += ctx->prof_flops[q / 2];
+    row->launches += 1;
   }
-  *seconds = s;
-  *flops = f;
-  *launches = (long long)(ctx->prof_used / 2);
   ctx->prof_used = 0;
   ctx->prof_flops.clear();
+  ctx->prof_family.clear();
+  ctx->prof_stage.clear();
+  return 0;
+}
+
+// GEMM-family view of profile_collect (kept for ekb200_gemm_profile): resets ALL families.
+int gemm_profile_collect(Ctx* ctx, double* seconds, double* flops, long long* launches) {
+  double s[PROF_FAMILIES], w[PROF_FAMILIES];
+  long long l[PROF_FAMILIES];
+  EKB_TRY(profile_collect(ctx, s, w, l));
+  *seconds = s[PROF_GEMM];
+  *flops = w[PROF_GEMM];
+  *launches = l[PROF_GEMM];
   return 0;
 }
 
 int gemm_batched(Ctx* ctx, int flags, const GemmP* d_batch, int nb, int max_m, int max_n) {
   if (nb <= 0 || max_m <= 0 || max_n <= 0) return 0;
   GemmP dummy = {};
-  if (max_n <= 64) return launch_cfg<128, 64, 32, 32, true>(ctx, flags, dummy, d_batch, nb, max_m, max_n, -1, 1);
-  return launch_cfg<128, 128, 64, 32, true>(ctx, flags, dummy, d_batch, nb, max_m, max_n, -1, 1);
+  EKB_TRY(prof_begin(ctx, PROF_GEMM_BATCHED, 0.0));  // FLOPs after deflation are only known on the device
+  int rc;
+  if (max_n <= 64) rc = launch_cfg<128, 64, 32, 32, true>(ctx, flags, dummy, d_batch, nb, max_m, max_n, -1, 1);
+  else rc = launch_cfg<128, 128, 64, 32, true>(ctx, flags, dummy, d_batch, nb, max_m, max_n, -1, 1);
+  if (rc) return rc;
+  return prof_end(ctx);
 }
 
 }  // namespace ekb

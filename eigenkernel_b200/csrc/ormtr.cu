@@ -424,6 +424,7 @@ static int q2_launch(Ctx* ctx, i64 n, const double* V2, i64 ldv, const double* T
     q2_consider<8>(ctx, k, ctx->q2_kc, &cost, &nw);
     const bool al16 = ((uintptr_t)Z & 15) == 0 && (ldz & 1) == 0;
     if (!al16) nw = -4;  // 8-byte global accesses: one generic instantiation
+    prof_begin(ctx, PROF_Q2_APPLY, 2.0 * (double)n * (double)n * (double)k);
     switch (nw) {
       case -4: ce = q2_apply_launch<B, NBS, 4, false>(ctx, packed, d_off, n, nS, Z, ldz, k); break;
       case 4: ce = q2_apply_launch<B, NBS, 4, true>(ctx, packed, d_off, n, nS, Z, ldz, k); break;
@@ -433,6 +434,7 @@ static int q2_launch(Ctx* ctx, i64 n, const double* V2, i64 ldv, const double* T
       case 8: ce = q2_apply_launch<B, NBS, 8, true>(ctx, packed, d_off, n, nS, Z, ldz, k); break;
       default: ce = cudaErrorInvalidValue;
     }
+    prof_end(ctx);
   }
   if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
   cleanup();

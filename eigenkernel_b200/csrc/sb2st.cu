@@ -216,11 +216,13 @@ int sb2st(Ctx* ctx, i64 n, int b, double* AB, i64 ldab, double* V2, i64 ldv, dou
     if (G > n - 2) G = (int)(n - 2);
     void* args[] = {(void*)&AB, (void*)&ldab, (void*)&n, (void*)&V2, (void*)&ldv, (void*)&TAU2, (void*)&ldtau,
                     (void*)&prog, (void*)&d, (void*)&e};
+    EKB_TRY(prof_begin(ctx, PROF_SB2ST, 12.0 * b * (double)n * (double)n));  // effective bytes, SURVEY 8(d)
     if (b == 64)
       EKB_CUDA(cudaLaunchCooperativeKernel((void*)sb2st_kernel<64>, dim3(G), dim3(64), args, smem, ctx->stream));
     else
       EKB_CUDA(cudaLaunchCooperativeKernel((void*)sb2st_kernel<32>, dim3(G), dim3(32), args, smem, ctx->stream));
     EKB_COUNT_LAUNCH(ctx);
+    EKB_TRY(prof_end(ctx));
   }
   extract_de_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(AB, ldab, n, d, e); EKB_COUNT_LAUNCH(ctx);
   EKB_CUDA(cudaGetLastError());

@@ -62,7 +62,7 @@ int syevd_dev(Ctx* ctx, i64 n, i64 nev, double* A, i64 lda, double* w, double* Z
     StageTimer t(ctx, "eigen_solver_b200:sy2sb");
     double* work = nullptr;
     EKB_TRY(sc.get((void**)&work, sy2sb_workspace_doubles(n, b, ctx->num_sms) * sizeof(double)));
-    int rc = sy2sb(ctx, n, b, A, lda, AB, ldab, T1, work);
+    int rc = ctx->nranks > 1 ? sy2sb_dist(ctx, n, b, A, lda, AB, ldab, T1) : sy2sb(ctx, n, b, A, lda, AB, ldab, T1, work);
     t.stop();
     sc.release(work);
     if (rc) return rc;

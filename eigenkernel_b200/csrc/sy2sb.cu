@@ -14,6 +14,8 @@
 // (ormtr.cu: apply_q1).
 #include <cooperative_groups.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
@@ -212,6 +214,17 @@ __global__ void pack_vw_kernel(const double* __restrict__ V, i64 ldv, const doub
   WV[(i64)(c + b) * ldp + i] = v;
 }
 
+static int launch_panel_qr(Ctx* ctx, int b, double* P, i64 ld, int m, double* tau, double* Rout, double* partial, int G) {
+  void* args[] = {(void*)&P, (void*)&ld, (void*)&m, (void*)&tau, (void*)&Rout, (void*)&partial};
+  EKB_TRY(prof_begin(ctx, PROF_PANEL_QR, 2.0 * m * (double)b * b));
+  if (b == 64)
+    EKB_CUDA(cudaLaunchCooperativeKernel((void*)panel_qr_kernel<64>, dim3(G), dim3(QR_THREADS), args, 0, ctx->stream));
+  else
+    EKB_CUDA(cudaLaunchCooperativeKernel((void*)panel_qr_kernel<32>, dim3(G), dim3(QR_THREADS), args, 0, ctx->stream));
+  EKB_COUNT_LAUNCH(ctx);
+  return prof_end(ctx);
+}
+
 static int pick_splitk(Ctx* ctx, i64 m, i64 n, i64 k, int bm, int bn) {
   i64 tiles = (i64)cdiv(m, bm) * cdiv(n, bn);
   i64 want = (2 * ctx->num_sms + tiles - 1) / tiles;
@@ -257,12 +270,7 @@ int sy2sb(Ctx* ctx, i64 n, int b, double* A, i64 lda, double* AB, i64 ldab, doub
       int G = (int)((m + QR_THREADS - 1) / QR_THREADS);
       if (G > ctx->num_sms) G = ctx->num_sms;
       int mi = (int)m;
-      void* args[] = {(void*)&P, (void*)&lda, (void*)&mi, (void*)&tau, (void*)&Rout, (void*)&partial};
-      if (b == 64)
-        EKB_CUDA(cudaLaunchCooperativeKernel((void*)panel_qr_kernel<64>, dim3(G), dim3(QR_THREADS), args, 0, ctx->stream));
-      else
-        EKB_CUDA(cudaLaunchCooperativeKernel((void*)panel_qr_kernel<32>, dim3(G), dim3(QR_THREADS), args, 0, ctx->stream));
-      EKB_COUNT_LAUNCH(ctx);
+      EKB_TRY(launch_panel_qr(ctx, b, P, lda, mi, tau, Rout, partial, G));
     }
     // 2. band extraction + explicit V
     fixup_extract_kernel<<<1, 256, 0, ctx->stream>>>(A, lda, n, j, b, Rout, AB, ldab); EKB_COUNT_LAUNCH(ctx);
@@ -301,6 +309,206 @@ int sy2sb(Ctx* ctx, i64 n, int b, double* A, i64 lda, double* AB, i64 ldab, doub
     EKB_CUDA(cudaGetLastError());
   }
   return 0;
+}
+
+// ------------------------------------------------------------------------------------------ sharded variant
+// The trailing matrix is dealt to the P ranks by block columns of width b, cyclically (block c -> rank c mod P),
+// stored compactly: Aloc is the local piece of a 1 x P block-cyclic distribution with NB = b -- the layout
+// setup_distributed_matrix (reference src/distribute_matrix.f90:92-148) builds, here with one GPU per process
+// column.  Owned columns are kept COMPLETE (both triangles), so per panel
+//   owner: Householder QR of its local block column, T, band columns -> one ncclBroadcast [T | AB | V];
+//   all:   partial W0 = A22(:, mine) V(mine, :)  (NN GEMM)          -> one ncclAllReduce of m x b;
+//          W from W0 (replicated b-wide work), A22(:, mine) -= [V W] [W(mine) V(mine)]^T  (K = 2b GEMM).
+// Every rank also keeps V_p in its full-size A (below the band) and T_p in T1: apply_q1 needs all panels.
+
+// global column of local column lc on rank r
+__device__ __host__ __forceinline__ i64 cyc_global_col(i64 lc, int b, int P, int r) {
+  return ((lc / b) * P + r) * (i64)b + lc % b;
+}
+
+__global__ void cyc_pack_kernel(const double* __restrict__ A, i64 lda, i64 n, int b, int P, int r, double* __restrict__ Aloc,
+                                i64 ldl, i64 nloc) {
+  const i64 lc = blockIdx.y;
+  if (lc >= nloc) return;
+  const i64 g = cyc_global_col(lc, b, P, r);
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x)
+    Aloc[lc * ldl + i] = A[g * lda + i];
+}
+
+// out(i, 0:b) = S1(g(lc0 + i) - row_base, 0:b), out(i, b:2b) = S2(same row, 0:b) (S2 may be null), i < nl
+__global__ void cyc_gather_rows_kernel(const double* __restrict__ S1, i64 ld1, const double* __restrict__ S2, i64 ld2, int b,
+                                       int P, int r, i64 lc0, i64 nl, i64 row_base, double* __restrict__ out, i64 ldo) {
+  const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.y;
+  if (i >= nl) return;
+  const i64 row = cyc_global_col(lc0 + i, b, P, r) - row_base;
+  out[(i64)c * ldo + i] = S1[(i64)c * ld1 + row];
+  if (S2) out[(i64)(c + b) * ldo + i] = S2[(i64)c * ld2 + row];
+}
+
+// VW = [V | W]  (m x 2b)
+__global__ void pack_vw_only_kernel(const double* __restrict__ V, i64 ldv, const double* __restrict__ W, i64 ldw, int m, int b,
+                                    double* __restrict__ VW, i64 ldp) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int c = blockIdx.y;
+  if (i >= m) return;
+  VW[(i64)c * ldp + i] = V[(i64)c * ldv + i];
+  VW[(i64)(c + b) * ldp + i] = W[(i64)c * ldw + i];
+}
+
+// tail(:, c) for the owned tail columns (global col j0 + c), zero elsewhere
+__global__ void cyc_tail_kernel(const double* __restrict__ Aloc, i64 ldl, i64 n, int b, int P, int r, i64 j0, i64 ncol,
+                                double* __restrict__ tail, i64 ldt) {
+  const i64 c = blockIdx.y;
+  if (c >= ncol) return;
+  const i64 g = j0 + c;
+  const bool mine = (int)((g / b) % P) == r;
+  const i64 lc = (g / b / P) * b + g % b;
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x)
+    tail[c * ldt + i] = mine ? Aloc[lc * ldl + i] : 0.0;
+}
+
+int sy2sb_dist(Ctx* ctx, i64 n, int b, double* A, i64 lda, double* AB, i64 ldab, double* T1) {
+  if (n <= 0) return 0;
+  const int P = ctx->nranks, r = ctx->rank;
+  const i64 nblk = (n + b - 1) / b;
+  const i64 myblk = nblk > r ? (nblk - r + P - 1) / P : 0;
+  i64 nloc = myblk * b;
+  if (myblk > 0 && (int)((nblk - 1) % P) == r) nloc -= nblk * b - n;  // ragged last block is mine
+  const i64 ldl = round_up(n, 8), ldp = ldl;
+  const i64 nlmax = nloc > 0 ? nloc : 1;
+  // workspaces
+  double *Aloc = nullptr, *X = nullptr, *W0 = nullptr, *VW = nullptr, *Vloc = nullptr, *WVloc = nullptr, *msg = nullptr,
+         *small = nullptr, *tail = nullptr;
+  std::vector<void*> owned;
+  auto get = [&](double** p, size_t doubles) {
+    int rc = ctx_alloc(ctx, (void**)p, doubles * sizeof(double));
+    if (rc == 0) owned.push_back(*p);
+    return rc;
+  };
+  auto cleanup = [&]() {
+    cudaStreamSynchronize(ctx->stream);
+    for (void* q : owned) ctx_free(ctx, q);
+  };
+  const size_t msg_doubles = (size_t)b * b + (size_t)ldab * b + (size_t)ldp * b;
+  int rc = get(&Aloc, (size_t)ldl * nlmax);
+  if (!rc) rc = get(&X, (size_t)ldp * b);
+  if (!rc) rc = get(&W0, (size_t)ldp * b);
+  if (!rc) rc = get(&VW, (size_t)ldp * 2 * b);
+  if (!rc) rc = get(&Vloc, (size_t)round_up(nlmax, 8) * b);
+  if (!rc) rc = get(&WVloc, (size_t)round_up(nlmax, 8) * 2 * b);
+  if (!rc) rc = get(&msg, msg_doubles);
+  if (!rc) rc = get(&small, (size_t)2 * ctx->num_sms * 64 + 8 * 64 * 64);
+  if (!rc) rc = get(&tail, (size_t)ldp * (b + 2));
+  if (rc) { cleanup(); return rc; }
+  double* partial = small;
+  double* tau = partial + 2 * ctx->num_sms * 64;
+  double* Rout = tau + 64;
+  double* Gm = Rout + 64 * 64;
+  double* S = Gm + 64 * 64;
+  double* TS = S + 64 * 64;
+  const i64 ldvl = round_up(nlmax, 8);
+
+  auto body = [&]() -> int {
+    if (nloc > 0) {
+      cyc_pack_kernel<<<dim3(std::min<i64>(cdiv(n, 256), 64), (unsigned)nloc), 256, 0, ctx->stream>>>(A, lda, n, b, P, r, Aloc,
+                                                                                                    ldl, nloc);
+      EKB_COUNT_LAUNCH(ctx);
+      EKB_CUDA(cudaGetLastError());
+    }
+    i64 j = 0;
+    int p = 0;
+    for (;; j += b, ++p) {
+      const i64 m = n - j - b;
+      if (m < 2) break;
+      const int owner = p % P;
+      const i64 mr = round_up(m, 8);
+      double* msgT = msg;
+      double* msgAB = msg + (size_t)b * b;
+      double* msgV = msgAB + (size_t)ldab * b;
+      if (r == owner) {
+        const i64 lb = p / P;
+        double* Pl = Aloc + (lb * b) * ldl + (j + b);
+        int G = (int)((m + QR_THREADS - 1) / QR_THREADS);
+        if (G > ctx->num_sms) G = ctx->num_sms;
+        EKB_TRY(launch_panel_qr(ctx, b, Pl, ldl, (int)m, tau, Rout, partial, G));
+        // band columns into the message (as if AB started at column j), V made explicit in place
+        fixup_extract_kernel<<<1, 256, 0, ctx->stream>>>(Aloc + (lb * b - j) * ldl, ldl, n, j, b, Rout, msgAB - j * ldab, ldab);
+        EKB_COUNT_LAUNCH(ctx);
+        EKB_CUDA(cudaGetLastError());
+        GemmP g;
+        g.m = b; g.n = b; g.k = (int)m; g.A = Pl; g.lda = ldl; g.B = Pl; g.ldb = ldl; g.C = Gm; g.ldc = b;
+        g.alpha = 1.0; g.beta = 0.0;
+        EKB_TRY(gemm(ctx, GEMM_TA, g, -1, pick_splitk(ctx, b, b, m, 128, 64)));
+        build_T_kernel<<<1, 64, 0, ctx->stream>>>(Gm, tau, b, msgT); EKB_COUNT_LAUNCH(ctx);
+        EKB_CUDA(cudaGetLastError());
+        EKB_TRY(copy_matrix(ctx, Pl, ldl, msgV, mr, m, b));
+      }
+      EKB_TRY(comm_bcast(ctx, msg, ((size_t)b * b + (size_t)ldab * b + (size_t)mr * b) * sizeof(double), owner));
+      double* Pv = A + j * lda + (j + b);  // V_p in the full-size array (apply_q1 reads it there)
+      double* T = T1 + (size_t)p * b * b;
+      EKB_TRY(copy_matrix(ctx, msgV, mr, Pv, lda, m, b));
+      EKB_TRY(copy_matrix(ctx, msgT, b, T, b, b, b));
+      EKB_TRY(copy_matrix(ctx, msgAB, ldab, AB + j * ldab, ldab, ldab, b));
+      // local trailing columns
+      const i64 lb0 = p >= r ? (p - r) / P + 1 : 0;
+      const i64 lc0 = lb0 * b;
+      const i64 nl = nloc > lc0 ? nloc - lc0 : 0;
+      double* Atr = Aloc + lc0 * ldl + (j + b);
+      GemmP g;
+      if (nl > 0) {
+        cyc_gather_rows_kernel<<<dim3(cdiv(nl, 256), b), 256, 0, ctx->stream>>>(Pv, lda, nullptr, 0, b, P, r, lc0, nl, j + b,
+                                                                               Vloc, ldvl);
+        EKB_COUNT_LAUNCH(ctx);
+        EKB_CUDA(cudaGetLastError());
+        g.m = (int)m; g.n = b; g.k = (int)nl; g.A = Atr; g.lda = ldl; g.B = Vloc; g.ldb = ldvl; g.C = W0; g.ldc = mr;
+        g.alpha = 1.0; g.beta = 0.0;
+        EKB_TRY(gemm(ctx, 0, g));
+      } else {
+        EKB_TRY(set_zero(ctx, W0, mr, mr, b));
+      }
+      EKB_TRY(comm_allreduce_sum(ctx, W0, (size_t)mr * b));
+      // X = W0 T ; S = V^T X ; TS = T^T S ; X -= 1/2 V TS  (X becomes W) -- replicated, identical on all ranks
+      g.m = (int)m; g.n = b; g.k = b; g.A = W0; g.lda = mr; g.B = T; g.ldb = b; g.C = X; g.ldc = ldp;
+      g.alpha = 1.0; g.beta = 0.0;
+      EKB_TRY(gemm(ctx, 0, g));
+      g.m = b; g.n = b; g.k = (int)m; g.A = Pv; g.lda = lda; g.B = X; g.ldb = ldp; g.C = S; g.ldc = b;
+      EKB_TRY(gemm(ctx, GEMM_TA, g, -1, pick_splitk(ctx, b, b, m, 128, 64)));
+      tts_kernel<<<1, 256, 0, ctx->stream>>>(T, S, b, TS); EKB_COUNT_LAUNCH(ctx);
+      EKB_CUDA(cudaGetLastError());
+      g.m = (int)m; g.n = b; g.k = b; g.A = Pv; g.lda = lda; g.B = TS; g.ldb = b; g.C = X; g.ldc = ldp;
+      g.alpha = -0.5; g.beta = 1.0;
+      EKB_TRY(gemm(ctx, 0, g));
+      if (nl > 0) {
+        pack_vw_only_kernel<<<dim3(cdiv(m, 256), b), 256, 0, ctx->stream>>>(Pv, lda, X, ldp, (int)m, b, VW, ldp);
+        EKB_COUNT_LAUNCH(ctx);
+        cyc_gather_rows_kernel<<<dim3(cdiv(nl, 256), b), 256, 0, ctx->stream>>>(X, ldp, Pv, lda, b, P, r, lc0, nl, j + b, WVloc,
+                                                                               ldvl);
+        EKB_COUNT_LAUNCH(ctx);
+        EKB_CUDA(cudaGetLastError());
+        // A22(:, mine) -= [V W] [W(mine) V(mine)]^T
+        g.m = (int)m; g.n = (int)nl; g.k = 2 * b; g.A = VW; g.lda = ldp; g.B = WVloc; g.ldb = ldvl; g.C = Atr; g.ldc = ldl;
+        g.alpha = -1.0; g.beta = 1.0;
+        EKB_TRY(gemm(ctx, GEMM_TB, g));
+      }
+    }
+    // tail columns j .. n-1 (at most b + 1 of them, possibly owned by two ranks): sum of the owners' copies
+    if (j < n) {
+      const i64 ncol = n - j;
+      cyc_tail_kernel<<<dim3(std::min<i64>(cdiv(n, 256), 64), (unsigned)ncol), 256, 0, ctx->stream>>>(Aloc, ldl, n, b, P, r, j, ncol,
+                                                                                                    tail, ldp);
+      EKB_COUNT_LAUNCH(ctx);
+      EKB_CUDA(cudaGetLastError());
+      EKB_TRY(comm_allreduce_sum(ctx, tail, (size_t)ldp * ncol));
+      extract_tail_kernel<<<(unsigned)ncol, 128, 0, ctx->stream>>>(tail - j * ldp, ldp, n, j, b, AB, ldab);
+      EKB_COUNT_LAUNCH(ctx);
+      EKB_CUDA(cudaGetLastError());
+    }
+    return 0;
+  };
+  rc = body();
+  cleanup();
+  return rc;
 }
 
 int sy2sb_num_panels(i64 n, int b) {

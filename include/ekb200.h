@@ -145,6 +145,15 @@ int64_t ekb200_num_launches(const ekb200_ctx* ctx);
 int ekb200_timer_start(ekb200_ctx* ctx);
 int ekb200_timer_stop(ekb200_ctx* ctx, double* seconds);
 int ekb200_gemm_profile(ekb200_ctx* ctx, double* seconds, double* flops, int64_t* launches);
+/* the same for every profiled kernel family; arrays of EKB200_PROF_FAMILIES entries, indexed by
+ * 0 GEMM engine (FLOPs) | 1 panel QR (FLOPs) | 2 Q2 apply (FLOPs) | 3 bulge chasing (effective bytes) |
+ * 4 batched merge GEMMs (work not counted: 0) | 5 NCCL exchanges (bytes).  Resets all families. */
+#define EKB200_PROF_FAMILIES 8
+int ekb200_kernel_profile(ekb200_ctx* ctx, double* seconds, double* work, int64_t* launches);
+/* (stage, family) breakdown of the last ekb200_kernel_profile / ekb200_gemm_profile call */
+int ekb200_profile_rows(const ekb200_ctx* ctx);
+int ekb200_profile_row(const ekb200_ctx* ctx, int i, const char** stage, int* family, double* seconds, double* work,
+                       int64_t* launches);
 
 /* ---- multi-GPU: ONE CONTEXT PER RANK, one rank per B200 (replaces the BLACS grid of src/processes.f90:17-65 and
  * the block-cyclic scatter of src/distribute_matrix.f90:92-148).  Rank 0 obtains a 128-byte id with
