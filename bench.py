@@ -170,6 +170,8 @@ def run_ours(args) -> None:
     local = int(os.environ.get("LOCAL_RANK", "0"))
     dist = None
     if world > 1:
+        # keep rank 0's stdout to the one JSON line: NCCL's version banner / warnings go to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch
         import torch.distributed as dist_mod
 

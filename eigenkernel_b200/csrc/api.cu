@@ -66,6 +66,8 @@ int ekb200_destroy(ekb200_ctx* h) {
   comm_destroy(ctx);
   for (void* p : ctx->allocs) cudaFree(p);
   ctx->allocs.clear();
+  ctx->live.clear();
+  ctx_trim(ctx);
   for (cudaEvent_t ev : ctx->prof_events) cudaEventDestroy(ev);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -99,6 +101,14 @@ int ekb200_set_option(ekb200_ctx* h, const char* key, int64_t value) {
   if (!strcmp(key, "q2_kc")) {
     if (value != 0 && (value < 64 || value > 128 || value % 16)) return -3;
     ctx->q2_kc = (int)value;
+    return 0;
+  }
+  if (!strcmp(key, "cache_device_memory")) {  // 0: release blocks to the driver at once; 1 (default): caching arena
+    ctx->cache_enabled = value != 0;
+    if (!ctx->cache_enabled) {
+      cudaStreamSynchronize(ctx->stream);
+      ctx_trim(ctx);
+    }
     return 0;
   }
   if (!strcmp(key, "profile_gemm")) {

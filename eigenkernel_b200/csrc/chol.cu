@@ -224,12 +224,112 @@ int potrf_lower(Ctx* ctx, i64 n, double* B, i64 ldb, double* invd) {
   return rc;
 }
 
-// A <- L^-1 A L^-T as two full triangular solves (2 n^3 FLOPs, all on the GEMM engine).
-// Requires the full symmetric A on entry; both triangles hold the result on exit.
+// ---------------------------------------------------------------- reduction to standard form
+// Leaf: A11 <- inv A11 inv^T for one diagonal block (nb <= 64); reads the lower triangle, writes BOTH triangles.
+__global__ void __launch_bounds__(256) sygst_leaf_kernel(double* __restrict__ A, i64 lda, int nb, const double* __restrict__ inv) {
+  extern __shared__ double dsm[];
+  double(*sa)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(dsm);
+  double(*si)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(dsm + NB * (NB + 1));
+  double(*st)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(dsm + 2 * NB * (NB + 1));
+  const int tid = threadIdx.x;
+  for (int e = tid; e < NB * NB; e += blockDim.x) {
+    const int r = e % NB, c = e / NB;
+    if (r >= c) {
+      const double x = (r < nb && c < nb) ? A[(i64)c * lda + r] : 0.0;
+      sa[r][c] = x;
+      sa[c][r] = x;
+    }
+    si[r][c] = inv[e];  // inv(r, c), lower triangular, zero padded
+  }
+  __syncthreads();
+  // T = inv * A  (inv lower: k <= r)
+  for (int e = tid; e < NB * NB; e += blockDim.x) {
+    const int r = e % NB, c = e / NB;
+    double acc = 0.0;
+    for (int k = 0; k <= r; ++k) acc += si[r][k] * sa[k][c];
+    st[r][c] = acc;
+  }
+  __syncthreads();
+  // R = T * inv^T : R(r, c) = sum_{k <= c} T(r, k) inv(c, k)
+  for (int e = tid; e < NB * NB; e += blockDim.x) {
+    const int r = e % NB, c = e / NB;
+    if (r < nb && c < nb) {
+      double acc = 0.0;
+      for (int k = 0; k <= c; ++k) acc += st[r][k] * si[c][k];
+      A[(i64)c * lda + r] = acc;
+    }
+  }
+}
+
+// C (m x n) -= M
+__global__ void sub_matrix_kernel(double* __restrict__ C, i64 ldc, const double* __restrict__ M, i64 ldm, i64 m, i64 n) {
+  i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  for (i64 j = blockIdx.y; j < n; j += gridDim.y) C[j * ldc + i] -= M[j * ldm + i];
+}
+
+// Recursive dsygst(itype = 1, 'L') on the LOWER triangle (n^3 FLOPs, all GEMM-shaped):
+//   A11 <- sygst(A11);  A21 <- A21 L11^-T;  M = 1/2 L21 A11;  A21 -= M;
+//   A22 -= A21 L21^T + L21 A21^T (lower);  A21 -= M;  A21 <- L22^-1 A21;  A22 <- sygst(A22).
+// Diagonal leaves come back with both triangles; every finished A11 is mirrored to full before it is used as the
+// symmetric factor of M.  Mws: scratch of at least ceil(n/2)^2 doubles (rounded to whole 64-blocks).
+static int sygst_rec(Ctx* ctx, i64 n, double* A, i64 lda, const double* L, i64 ldl, const double* invd, double* tmp,
+                     double* Mws) {
+  if (n <= 0) return 0;
+  if (n <= NB) {
+    static bool attr = false;
+    constexpr size_t smem = 3 * NB * (NB + 1) * sizeof(double);
+    if (!attr) {
+      EKB_CUDA(cudaFuncSetAttribute(sygst_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr = true;
+    }
+    sygst_leaf_kernel<<<1, 256, smem, ctx->stream>>>(A, lda, (int)n, invd); EKB_COUNT_LAUNCH(ctx);
+    EKB_CUDA(cudaGetLastError());
+    return 0;
+  }
+  const i64 nblk = (n + NB - 1) / NB;
+  const i64 n1 = ((nblk + 1) / 2) * NB, n2 = n - n1;
+  double* A21 = A + n1;
+  double* A22 = A + n1 * lda + n1;
+  const double* L21 = L + n1;
+  const double* L22 = L + n1 * ldl + n1;
+  const double* inv2 = invd + (n1 / NB) * NB * NB;
+  EKB_TRY(sygst_rec(ctx, n1, A, lda, L, ldl, invd, tmp, Mws));
+  if (n1 > NB) EKB_TRY(symmetrize_from_lower(ctx, A, lda, n1));
+  EKB_TRY(trsm_rec(ctx, TRSM_RLT, n2, n1, L, ldl, invd, A21, lda, tmp));
+  GemmP p;
+  p.m = (int)n2; p.n = (int)n1; p.k = (int)n1;
+  p.A = L21; p.lda = ldl; p.B = A; p.ldb = lda; p.C = Mws; p.ldc = n2;
+  p.alpha = 0.5; p.beta = 0.0;
+  EKB_TRY(gemm(ctx, 0, p));
+  dim3 grid(cdiv(n2, 256), (unsigned)(n1 < 32768 ? n1 : 32768));
+  sub_matrix_kernel<<<grid, 256, 0, ctx->stream>>>(A21, lda, Mws, n2, n2, n1); EKB_COUNT_LAUNCH(ctx);
+  EKB_CUDA(cudaGetLastError());
+  p.m = (int)n2; p.n = (int)n2; p.k = (int)n1; p.alpha = -1.0; p.beta = 1.0; p.C = A22; p.ldc = lda;
+  p.A = A21; p.lda = lda; p.B = L21; p.ldb = ldl;
+  EKB_TRY(gemm(ctx, GEMM_TB, p, /*tri_keep=*/1));
+  p.A = L21; p.lda = ldl; p.B = A21; p.ldb = lda;
+  EKB_TRY(gemm(ctx, GEMM_TB, p, /*tri_keep=*/1));
+  sub_matrix_kernel<<<grid, 256, 0, ctx->stream>>>(A21, lda, Mws, n2, n2, n1); EKB_COUNT_LAUNCH(ctx);
+  EKB_CUDA(cudaGetLastError());
+  EKB_TRY(trsm_rec(ctx, TRSM_LLN, n2, n1, L22, ldl, inv2, A21, lda, tmp));
+  return sygst_rec(ctx, n2, A22, lda, L22, ldl, inv2, tmp, Mws);
+}
+
+// A <- L^-1 A L^-T (pdsygst(1,'L')).  Reads the lower triangle of A; both triangles hold the result on exit.
 int sygst_lower(Ctx* ctx, i64 n, double* A, i64 lda, const double* L, i64 ldl, const double* invd) {
-  EKB_TRY(trsm_lower(ctx, TRSM_LLN, n, n, L, ldl, invd, A, lda));
-  EKB_TRY(trsm_lower(ctx, TRSM_RLT, n, n, L, ldl, invd, A, lda));
-  return 0;
+  if (n <= 0) return 0;
+  const i64 nblk = (n + NB - 1) / NB;
+  const i64 h = ((nblk + 1) / 2) * NB;
+  double *tmp = nullptr, *Mws = nullptr;
+  EKB_TRY(ctx_alloc(ctx, (void**)&tmp, (size_t)round_up(n, 2) * NB * sizeof(double)));
+  int rc = ctx_alloc(ctx, (void**)&Mws, (size_t)h * h * sizeof(double));
+  if (!rc) rc = sygst_rec(ctx, n, A, lda, L, ldl, invd, tmp, Mws);
+  if (!rc) rc = symmetrize_from_lower(ctx, A, lda, n);
+  cudaStreamSynchronize(ctx->stream);
+  ctx_free(ctx, tmp);
+  if (Mws) ctx_free(ctx, Mws);
+  return rc;
 }
 
 }  // namespace ekb

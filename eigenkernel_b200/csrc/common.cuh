@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "layout.h"
@@ -31,7 +32,11 @@ struct Ctx {
   int num_sms = 148;
   cudaStream_t stream = nullptr;
   std::vector<Event> events;          // timing table replayed through add_event by the caller
-  std::vector<void*> allocs;          // every device allocation owned by the context
+  std::vector<void*> allocs;          // every device allocation handed out and not yet released
+  std::vector<std::pair<void*, size_t>> live;   // ... with its (rounded) size
+  std::vector<std::pair<void*, size_t>> cache;  // released blocks kept for reuse (caching arena, context.cu)
+  size_t cached_bytes = 0;
+  bool cache_enabled = true;
   cudaError_t last_cuda = cudaSuccess;
   // scratch
   double* splitk_ws = nullptr;        // split-K partial sums
@@ -80,6 +85,7 @@ struct Ctx {
 
 int ctx_alloc(Ctx* ctx, void** p, size_t bytes);
 int ctx_free(Ctx* ctx, void* p);
+void ctx_trim(Ctx* ctx);  // return every cached block to the driver
 void ctx_add_event(Ctx* ctx, const char* name, double seconds);
 
 // Scoped stage timer on the context stream (CUDA events, device time).

@@ -92,6 +92,45 @@ __device__ __forceinline__ void load_tile(double* s, const double* __restrict__ 
   }
 }
 
+// ---- interior fast path: the whole (BMN x BK) tile is in range and 16-byte aligned, so a thread's copies differ
+// from one another (and from one k-tile to the next) only by compile-time strides; dst/src already carry the
+// thread's own offset.
+__device__ __forceinline__ void cp_async16_full(unsigned s, const double* g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(g) : "memory");
+}
+template <int BMN>
+__device__ __forceinline__ void load_tile_fast_km(unsigned dst, const double* __restrict__ src, i64 ld) {
+  constexpr int RPP = GEMM_THREADS / (BK / 2);  // tile rows (mn) covered per pass
+#pragma unroll
+  for (int q = 0; q < BMN / RPP; ++q) cp_async16_full(dst + q * RPP * LDK * 8, src + (i64)q * RPP * ld);
+}
+template <int BMN>
+__device__ __forceinline__ void load_tile_fast_mn(unsigned dst, const double* __restrict__ src, i64 ld) {
+  constexpr int KPP = GEMM_THREADS / (BMN / 2);  // k rows covered per pass
+#pragma unroll
+  for (int q = 0; q < BK / KPP; ++q) cp_async16_full(dst + q * KPP * (BMN + 4) * 8, src + (i64)q * KPP * ld);
+}
+
+// One k-tile of DMMAs with compile-time shared-memory strides (immediate LDS offsets, no address arithmetic).
+template <int MI, int NI, int BM, int BN, bool AKM, bool BKM>
+__device__ __forceinline__ void mma_ktile(double (&acc)[MI][NI][2], const double* __restrict__ tA,
+                                          const double* __restrict__ tB) {
+  constexpr int a_smn = AKM ? LDK : 1, a_sk = AKM ? 1 : (BM + 4);
+  constexpr int b_smn = BKM ? LDK : 1, b_sk = BKM ? 1 : (BN + 4);
+#pragma unroll
+  for (int kk = 0; kk < BK / 4; ++kk) {
+    double af[MI], bf[NI];
+#pragma unroll
+    for (int i = 0; i < MI; ++i) af[i] = tA[i * 8 * a_smn + kk * 4 * a_sk];
+#pragma unroll
+    for (int j = 0; j < NI; ++j) bf[j] = tB[j * 8 * b_smn + kk * 4 * b_sk];
+#pragma unroll
+    for (int i = 0; i < MI; ++i)
+#pragma unroll
+      for (int j = 0; j < NI; ++j) dmma884(acc[i][j][0], acc[i][j][1], bf[j], af[i]);
+  }
+}
+
 template <int BM, int BN, int WM, int WN, bool BATCHED>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(GemmP p0, const GemmP* __restrict__ batch, int flags, int tri_keep, int splitk, double* __restrict__ ws) {
@@ -137,10 +176,37 @@ gemm_kernel(GemmP p0, const GemmP* __restrict__ batch, int flags, int tri_keep, 
     if (syma) return (kt * BK) >= m0 + BM;
     return ta;
   };
+  // per-thread pieces of the interior fast path (see load_tile_fast_*)
+  const bool a_full = al16 && (m0 + BM <= p.m);
+  const bool b_full = al16 && (n0 + BN <= p.n);
+  const unsigned sA32 = (unsigned)__cvta_generic_to_shared(sA), sB32 = (unsigned)__cvta_generic_to_shared(sB);
+  const int r_km = tid / (BK / 2), kc_km = (tid % (BK / 2)) * 2;
+  const i64 a_g_km = (i64)(m0 + r_km) * p.lda + kc_km;             // + k0
+  const unsigned a_s_km = (unsigned)(r_km * LDK + kc_km) * 8u;
+  const int a_k_mn = tid / (BM / 2), a_m_mn = (tid % (BM / 2)) * 2;
+  const i64 a_g_mn = (i64)a_k_mn * p.lda + m0 + a_m_mn;            // + k0 * lda
+  const unsigned a_s_mn = (unsigned)(a_k_mn * (BM + 4) + a_m_mn) * 8u;
+  const int b_k_mn = tid / (BN / 2), b_n_mn = (tid % (BN / 2)) * 2;
+  const i64 b_g = b_kmajor ? (i64)(n0 + r_km) * p.ldb + kc_km : (i64)b_k_mn * p.ldb + n0 + b_n_mn;
+  const unsigned b_s = (b_kmajor ? (unsigned)(r_km * LDK + kc_km) : (unsigned)(b_k_mn * (BN + 4) + b_n_mn)) * 8u;
   auto issue = [&](int kt, int stage) {
     const int k0 = kt * BK;
-    load_tile<BM>(sA + stage * A_TILE, p.A, p.lda, a_is_kmajor(kt), al16, m0, k0, p.m, p.k, tid);
-    load_tile<BN>(sB + stage * B_TILE, p.B, p.ldb, b_kmajor, al16, n0, k0, p.n, p.k, tid);
+    const bool kfull = k0 + BK <= p.k;
+    const bool akm = a_is_kmajor(kt);
+    if (a_full && kfull) {
+      const unsigned st = sA32 + (unsigned)(stage * A_TILE) * 8u;
+      if (akm) load_tile_fast_km<BM>(st + a_s_km, p.A + a_g_km + k0, p.lda);
+      else load_tile_fast_mn<BM>(st + a_s_mn, p.A + a_g_mn + (i64)k0 * p.lda, p.lda);
+    } else {
+      load_tile<BM>(sA + stage * A_TILE, p.A, p.lda, akm, al16, m0, k0, p.m, p.k, tid);
+    }
+    if (b_full && kfull) {
+      const unsigned st = sB32 + (unsigned)(stage * B_TILE) * 8u;
+      if (b_kmajor) load_tile_fast_km<BN>(st + b_s, p.B + b_g + k0, p.ldb);
+      else load_tile_fast_mn<BN>(st + b_s, p.B + b_g + (i64)k0 * p.ldb, p.ldb);
+    } else {
+      load_tile<BN>(sB + stage * B_TILE, p.B, p.ldb, b_kmajor, al16, n0, k0, p.n, p.k, tid);
+    }
   };
 
   double acc[MI][NI][2];
@@ -155,8 +221,9 @@ gemm_kernel(GemmP p0, const GemmP* __restrict__ batch, int flags, int tri_keep, 
     cp_async_commit();
   }
 
-  const int b_smn = b_kmajor ? LDK : 1, b_sk = b_kmajor ? 1 : (BN + 4);
-  const int b_off = (wn * WN + lq) * b_smn + lr * b_sk;
+  // thread offsets of the fragment loads for either layout of each operand
+  const int a_t_km = (wm * WM + lq) * LDK + lr, a_t_mn = (wm * WM + lq) + lr * (BM + 4);
+  const int b_t = b_kmajor ? (wn * WN + lq) * LDK + lr : (wn * WN + lq) + lr * (BN + 4);
 
   for (int it = 0; it < nk; ++it) {
     cp_async_wait<GEMM_STAGES - 2>();
@@ -168,20 +235,14 @@ gemm_kernel(GemmP p0, const GemmP* __restrict__ batch, int flags, int tri_keep, 
     }
     const int stage = it % GEMM_STAGES;
     const bool akm = a_is_kmajor(kt_begin + it);
-    const int a_smn = akm ? LDK : 1, a_sk = akm ? 1 : (BM + 4);
-    const double* tA = sA + stage * A_TILE + (wm * WM + lq) * a_smn + lr * a_sk;
-    const double* tB = sB + stage * B_TILE + b_off;
-#pragma unroll
-    for (int kk = 0; kk < BK / 4; ++kk) {
-      double af[MI], bf[NI];
-#pragma unroll
-      for (int i = 0; i < MI; ++i) af[i] = tA[i * 8 * a_smn + kk * 4 * a_sk];
-#pragma unroll
-      for (int j = 0; j < NI; ++j) bf[j] = tB[j * 8 * b_smn + kk * 4 * b_sk];
-#pragma unroll
-      for (int i = 0; i < MI; ++i)
-#pragma unroll
-        for (int j = 0; j < NI; ++j) dmma884(acc[i][j][0], acc[i][j][1], bf[j], af[i]);
+    const double* tA = sA + stage * A_TILE + (akm ? a_t_km : a_t_mn);
+    const double* tB = sB + stage * B_TILE + b_t;
+    if (akm) {
+      if (b_kmajor) mma_ktile<MI, NI, BM, BN, true, true>(acc, tA, tB);
+      else mma_ktile<MI, NI, BM, BN, true, false>(acc, tA, tB);
+    } else {
+      if (b_kmajor) mma_ktile<MI, NI, BM, BN, false, true>(acc, tA, tB);
+      else mma_ktile<MI, NI, BM, BN, false, false>(acc, tA, tB);
     }
   }
   cp_async_wait<0>();

@@ -3,7 +3,7 @@
 // sy2sb.cu this replaces pdsytrd('L'), reference src/solver_scalapack_all.f90:59, and the gather of d/e
 // (allgather_row_wise, src/distribute_matrix.f90:431-478; solver_scalapack_all.f90:75-78).
 //
-// One CTA owns one sweep at a time and keeps the sweep's moving b x b window in shared memory; sweeps are
+// One CTA (4 b threads) owns one sweep at a time and keeps the sweep's moving b x b window in shared memory; sweeps are
 // pipelined across the resident CTAs through per-sweep progress counters in global memory (sweep s may
 // run task t once sweep s-1 has finished task t+2).  The band lives in L2 (8*2b*n bytes = 32 MiB at
 // n = 32768, b = 64); reflectors stream out to HBM in the layout the back-transformation consumes:
@@ -21,11 +21,27 @@ __host__ __device__ __forceinline__ int sb2st_num_tasks(i64 n, int b, i64 s) {
   return (int)((n - 3 - s) / b) + 1;
 }
 
+__device__ __forceinline__ void bar_named(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+// 4 B threads per CTA, split into four groups of B threads (whole warps) that work on the three blocks of the
+// window CONCURRENTLY once the reflector is known:
+//   group 0: left-apply H on the L block and stream it back (final for this sweep);
+//   group 1: two-sided update of the diagonal block D (p = tau D v, w = p - tau/2 (p.v) v), then -- together with
+//   group 3 -- D -= v w^T + w v^T written straight back to the band (even / odd columns);
+//   group 2: right-apply on the B block (u = tau B v, B -= u v^T), which becomes the L block of the next task.
+// All global loads of a task (D and B blocks, 2 * B/4 independent loads per thread) are issued before the first
+// use, so a task pays ONE L2 round trip instead of 2 B dependent ones; the reflector itself is formed by a
+// single warp (shuffle reduction, no block barrier).
 template <int B>
-__global__ void __launch_bounds__(B) sb2st_kernel(double* __restrict__ AB, i64 ldab, i64 n, double* __restrict__ V2,
-                                                  i64 ldv, double* __restrict__ TAU2, int ldtau, int* __restrict__ prog,
-                                                  double* __restrict__ d_out, double* __restrict__ e_out) {
+__global__ void __launch_bounds__(4 * B) sb2st_kernel(double* __restrict__ AB, i64 ldab, i64 n, double* __restrict__ V2,
+                                                      i64 ldv, double* __restrict__ TAU2, int ldtau, int* __restrict__ prog,
+                                                      double* __restrict__ d_out, double* __restrict__ e_out) {
   constexpr int LDS = B + 1;
+  constexpr int CPT = B / 4;        // columns of D / B loaded per thread
+  constexpr int EPL = B / 32;       // reflector elements per lane of warp 0
+  constexpr int WPG = B / 32;       // warps per group
   extern __shared__ double sm[];
   double* buf0 = sm;                 // L / B blocks alternate between buf0 and buf1
   double* buf1 = sm + B * LDS;
@@ -33,8 +49,10 @@ __global__ void __launch_bounds__(B) sb2st_kernel(double* __restrict__ AB, i64 l
   double* v = sm + 3 * B * LDS;      // B
   double* w = v + B;                 // B
   __shared__ double red[4];
-  __shared__ double s_tau, s_beta, s_scal;
+  __shared__ double s_tau;
   const int tid = threadIdx.x;
+  const int grp = tid / B, li = tid % B;
+  const int lane = tid & 31;
   const int G = gridDim.x;
 
   for (i64 s = blockIdx.x; s <= n - 3; s += G) {
@@ -54,118 +72,136 @@ __global__ void __launch_bounds__(B) sb2st_kernel(double* __restrict__ AB, i64 l
         }
         __syncthreads();
       }
-      // ---- load
-      if (t == 0) {
-        // L block is just column s: rows s+1..s+nr (offsets 1..nr)
-        if (tid < nr) bufL[tid] = __ldcg(AB + s * ldab + 1 + tid);
-      }
-      // D block: A(R,R), lower stored; mirror into full
-      for (int jj = 0; jj < nr; ++jj) {
-        const int ii = tid;
-        if (ii >= jj && ii < nr) {
-          double x = __ldcg(AB + (r0 + jj) * ldab + (ii - jj));
-          bufD[jj * LDS + ii] = x;
-          bufD[ii * LDS + jj] = x;
+      // ---- load: every thread issues its 2 * CPT independent loads, then stores them to shared memory
+      {
+        double xd[CPT], xb[CPT];
+#pragma unroll
+        for (int q = 0; q < CPT; ++q) {
+          const int jj = grp + 4 * q;
+          const double* col = AB + (r0 + jj) * ldab;
+          xd[q] = (jj < nr && li >= jj && li < nr) ? __ldcg(col + (li - jj)) : 0.0;
+          xb[q] = (jj < nr && li < nr2) ? __ldcg(col + (B + li - jj)) : 0.0;
         }
-      }
-      // B block: A(R+B, R): element (ii,jj) at offset B + ii - jj of column r0+jj
-      for (int jj = 0; jj < nr; ++jj) {
-        const int ii = tid;
-        if (ii < nr2) bufB[jj * LDS + ii] = __ldcg(AB + (r0 + jj) * ldab + (B + ii - jj));
+        if (t == 0 && grp == 0 && li < nr) bufL[li] = __ldcg(AB + s * ldab + 1 + li);  // L block = column s
+#pragma unroll
+        for (int q = 0; q < CPT; ++q) {
+          const int jj = grp + 4 * q;
+          if (jj < nr && li >= jj && li < nr) {  // D block: A(R,R), lower stored; mirrored into full
+            bufD[jj * LDS + li] = xd[q];
+            bufD[li * LDS + jj] = xd[q];
+          }
+          if (jj < nr && li < nr2) bufB[jj * LDS + li] = xb[q];  // B block: A(R+B, R)
+        }
       }
       __syncthreads();
-      // ---- 1. reflector from x = bufL(0:nr, 0)
-      {
-        double xi = (tid > 0 && tid < nr) ? bufL[tid] : 0.0;
-        double sq = xi * xi;
+      // ---- 1. reflector from x = bufL(0:nr, 0), by warp 0 alone
+      if (tid < 32) {
+        double xs[EPL];
+        double sq = 0.0;
+#pragma unroll
+        for (int q = 0; q < EPL; ++q) {
+          const int e = lane + 32 * q;
+          xs[q] = (e > 0 && e < nr) ? bufL[e] : 0.0;
+          sq += xs[q] * xs[q];
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-        if ((tid & 31) == 0) red[tid >> 5] = sq;
-        __syncthreads();
-        if (tid == 0) {
-          double xn2 = 0.0;
-          for (int q = 0; q < B / 32; ++q) xn2 += red[q];
-          double alpha = bufL[0];
-          double beta, tau, sc;
-          if (xn2 == 0.0) {
-            beta = alpha; tau = 0.0; sc = 0.0;
-          } else {
-            beta = -copysign(sqrt(alpha * alpha + xn2), alpha);
-            tau = (beta - alpha) / beta;
-            sc = 1.0 / (alpha - beta);
-          }
-          s_tau = tau; s_beta = beta; s_scal = sc;
+        const double alpha = bufL[0];
+        double beta, tau, sc;
+        if (sq == 0.0) {
+          beta = alpha; tau = 0.0; sc = 0.0;
+        } else {
+          beta = -copysign(sqrt(alpha * alpha + sq), alpha);
+          tau = (beta - alpha) / beta;
+          sc = 1.0 / (alpha - beta);
+        }
+        __syncwarp();
+        if (lane == 0) {
+          s_tau = tau;
           TAU2[(i64)s * ldtau + t] = tau;
         }
-        __syncthreads();
-        const double sc = s_scal;
-        double vi = 0.0;
-        if (tid == 0) vi = 1.0;
-        else if (tid < nr) vi = xi * sc;
-        v[tid] = vi;
-        if (tid < nr) V2[s * ldv + r0 + tid] = vi;
-        if (tid == 0) bufL[0] = s_beta;
-        else if (tid < nr) bufL[tid] = 0.0;
+#pragma unroll
+        for (int q = 0; q < EPL; ++q) {
+          const int e = lane + 32 * q;
+          const double vi = (e == 0) ? 1.0 : (e < nr ? xs[q] * sc : 0.0);
+          v[e] = vi;
+          if (e < nr) {
+            V2[s * ldv + r0 + e] = vi;
+            bufL[e] = (e == 0) ? beta : 0.0;
+          }
+        }
       }
       __syncthreads();
       const double tau = s_tau;
-      // ---- 2. left-apply H to bufL(:, 1:B) (t >= 1), thread per column
-      if (t >= 1) {
-        const int jj = tid;
-        if (jj >= 1) {
-          double dot = 0.0;
-          for (int ii = 0; ii < nr; ++ii) dot += v[ii] * bufL[jj * LDS + ii];
-          dot *= tau;
-          for (int ii = 0; ii < nr; ++ii) bufL[jj * LDS + ii] -= dot * v[ii];
+      if (grp == 0) {
+        // ---- 2. left-apply H to bufL(:, 1:B) (t >= 1), thread per column; then write the L block back
+        if (t >= 1) {
+          const int jj = li;
+          if (jj >= 1) {
+            double dot = 0.0;
+#pragma unroll 8
+            for (int ii = 0; ii < nr; ++ii) dot += v[ii] * bufL[jj * LDS + ii];
+            dot *= tau;
+#pragma unroll 8
+            for (int ii = 0; ii < nr; ++ii) bufL[jj * LDS + ii] -= dot * v[ii];
+          }
+          bar_named(1, B);
+          if (li < nr) {
+#pragma unroll 8
+            for (int jj2 = 0; jj2 < B; ++jj2) AB[(r0 - B + jj2) * ldab + (B + li - jj2)] = bufL[jj2 * LDS + li];
+          }
+        } else {
+          if (li < nr) AB[s * ldab + 1 + li] = bufL[li];
         }
-      }
-      // ---- 4. two-sided on D: p = tau D v (thread per row)
-      double pi = 0.0;
-      if (tid < nr) {
-        for (int jj = 0; jj < nr; ++jj) pi += bufD[jj * LDS + tid] * v[jj];
-        pi *= tau;
-      }
-      {
-        double pv = (tid < nr) ? pi * v[tid] : 0.0;
+      } else if (grp == 1) {
+        // ---- 3. two-sided on D: p = tau D v (thread per row), w = p - tau/2 (p.v) v
+        double pi = 0.0;
+        if (li < nr) {
+#pragma unroll 8
+          for (int jj = 0; jj < nr; ++jj) pi += bufD[jj * LDS + li] * v[jj];
+          pi *= tau;
+        }
+        const double vl = v[li];
+        double pv = (li < nr) ? pi * vl : 0.0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) pv += __shfl_xor_sync(0xffffffffu, pv, o);
-        __syncthreads();  // red reuse + bufL column updates complete
-        if ((tid & 31) == 0) red[tid >> 5] = pv;
-        __syncthreads();
+        if (lane == 0) red[li >> 5] = pv;
+        bar_named(3, B);
         double ptv = 0.0;
-        for (int q = 0; q < B / 32; ++q) ptv += red[q];
-        const double wi = (tid < nr) ? pi - 0.5 * tau * ptv * v[tid] : 0.0;
-        w[tid] = wi;
-      }
-      __syncthreads();
-      // ---- 3. write back L block (final for this sweep)
-      if (t == 0) {
-        if (tid < nr) AB[s * ldab + 1 + tid] = bufL[tid];
+#pragma unroll
+        for (int q = 0; q < WPG; ++q) ptv += red[q];
+        const double wi = (li < nr) ? pi - 0.5 * tau * ptv * vl : 0.0;
+        w[li] = wi;
+        bar_named(2, 2 * B);
+        // D -= v w^T + w v^T, even columns, lower part straight back to the band
+        if (li < nr) {
+#pragma unroll 4
+          for (int jj = 0; jj <= li; jj += 2)
+            AB[(r0 + jj) * ldab + (li - jj)] = bufD[jj * LDS + li] - vl * w[jj] - wi * v[jj];
+        }
+      } else if (grp == 3) {
+        bar_named(2, 2 * B);
+        if (li < nr) {
+          const double vl = v[li], wi = w[li];
+#pragma unroll 4
+          for (int jj = 1; jj <= li; jj += 2)
+            AB[(r0 + jj) * ldab + (li - jj)] = bufD[jj * LDS + li] - vl * w[jj] - wi * v[jj];
+        }
       } else {
-        for (int jj = 0; jj < B; ++jj) {
-          const int ii = tid;
-          if (ii < nr) AB[(r0 - B + jj) * ldab + (B + ii - jj)] = bufL[jj * LDS + ii];
+        // ---- 4. right-apply on B: u = tau B v (thread per row), B -= u v^T
+        if (li < nr2) {
+          double u = 0.0;
+#pragma unroll 8
+          for (int jj = 0; jj < nr; ++jj) u += bufB[jj * LDS + li] * v[jj];
+          u *= tau;
+#pragma unroll 8
+          for (int jj = 0; jj < nr; ++jj) bufB[jj * LDS + li] -= u * v[jj];
+          // the B block becomes the L block of task t+1 (same sweep); if there is no task t+1 it must be stored
+          if (t + 1 >= ntask) {
+#pragma unroll 8
+            for (int jj = 0; jj < nr; ++jj) AB[(r0 + jj) * ldab + (B + li - jj)] = bufB[jj * LDS + li];
+          }
         }
-      }
-      // D -= v w^T + w v^T (thread per row), write back lower part
-      if (tid < nr) {
-        const double vi = v[tid], wi = w[tid];
-        for (int jj = 0; jj <= tid; ++jj) {
-          double x = bufD[jj * LDS + tid] - vi * w[jj] - wi * v[jj];
-          AB[(r0 + jj) * ldab + (tid - jj)] = x;
-        }
-      }
-      // ---- 6. right-apply on B: u = B v (thread per row), B -= tau u v^T
-      if (tid < nr2) {
-        double u = 0.0;
-        for (int jj = 0; jj < nr; ++jj) u += bufB[jj * LDS + tid] * v[jj];
-        u *= tau;
-        for (int jj = 0; jj < nr; ++jj) bufB[jj * LDS + tid] -= u * v[jj];
-      }
-      // the B block becomes the L block of task t+1 (same sweep); if there is no task t+1 it must be stored
-      if (t + 1 >= ntask) {
-        if (tid < nr2)
-          for (int jj = 0; jj < nr; ++jj) AB[(r0 + jj) * ldab + (B + tid - jj)] = bufB[jj * LDS + tid];
       }
       // ---- publish progress
       __threadfence();
@@ -201,12 +237,12 @@ int sb2st(Ctx* ctx, i64 n, int b, double* AB, i64 ldab, double* V2, i64 ldv, dou
     if (b == 64) {
       EKB_CUDA(cudaFuncSetAttribute(sb2st_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       int per_sm = 0;
-      EKB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sb2st_kernel<64>, 64, smem));
+      EKB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sb2st_kernel<64>, 256, smem));
       G = per_sm * ctx->num_sms;
     } else {
       EKB_CUDA(cudaFuncSetAttribute(sb2st_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       int per_sm = 0;
-      EKB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sb2st_kernel<32>, 32, smem));
+      EKB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sb2st_kernel<32>, 128, smem));
       G = per_sm * ctx->num_sms;
     }
     if (G < 1) return EKB_ERR_INTERNAL;
@@ -218,9 +254,9 @@ int sb2st(Ctx* ctx, i64 n, int b, double* AB, i64 ldab, double* V2, i64 ldv, dou
                     (void*)&prog, (void*)&d, (void*)&e};
     EKB_TRY(prof_begin(ctx, PROF_SB2ST, 12.0 * b * (double)n * (double)n));  // effective bytes, SURVEY 8(d)
     if (b == 64)
-      EKB_CUDA(cudaLaunchCooperativeKernel((void*)sb2st_kernel<64>, dim3(G), dim3(64), args, smem, ctx->stream));
+      EKB_CUDA(cudaLaunchCooperativeKernel((void*)sb2st_kernel<64>, dim3(G), dim3(256), args, smem, ctx->stream));
     else
-      EKB_CUDA(cudaLaunchCooperativeKernel((void*)sb2st_kernel<32>, dim3(G), dim3(32), args, smem, ctx->stream));
+      EKB_CUDA(cudaLaunchCooperativeKernel((void*)sb2st_kernel<32>, dim3(G), dim3(128), args, smem, ctx->stream));
     EKB_COUNT_LAUNCH(ctx);
     EKB_TRY(prof_end(ctx));
   }

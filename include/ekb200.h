@@ -29,7 +29,8 @@ int ekb200_create(ekb200_ctx** ctx, int device);
 int ekb200_destroy(ekb200_ctx* ctx);
 const char* ekb200_strerror(int info);
 const char* ekb200_last_error(const ekb200_ctx* ctx);
-int ekb200_set_option(ekb200_ctx* ctx, const char* key, int64_t value); /* "band" = half bandwidth b (32|64); "profile_gemm" = 0|1 */
+int ekb200_set_option(ekb200_ctx* ctx, const char* key, int64_t value); /* "band" = half bandwidth b (32|64); "profile_gemm" = 0|1;
+                                                                           "cache_device_memory" = 1|0 (caching arena; 0 also trims) */
 int ekb200_version(void);
 
 /* ---- timing table (replaces add_event, src/event_logger.f90:23-65; seconds are CUDA-event times) */

@@ -10,6 +10,10 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize("ta,tb,m,n,k", [
     ("N", "N", 256, 256, 256), ("N", "T", 300, 200, 100), ("T", "N", 129, 257, 65), ("T", "T", 64, 64, 64),
     ("N", "N", 1, 1, 1), ("N", "N", 1000, 37, 513), ("T", "N", 37, 1000, 2049), ("N", "T", 511, 513, 17),
+    # interior fast path (full 128x128 / 128x64 / 64x128 tiles, full k-tiles) next to ragged edges and k tails
+    ("N", "N", 1024, 768, 512), ("N", "T", 1024, 768, 512), ("T", "N", 1024, 768, 512), ("T", "T", 1024, 768, 512),
+    ("N", "N", 1100, 700, 500), ("N", "T", 1100, 700, 500), ("T", "N", 1100, 700, 500), ("T", "T", 1100, 700, 500),
+    ("N", "N", 2048, 64, 1000), ("T", "N", 64, 2048, 1000), ("N", "T", 2048, 64, 136), ("T", "T", 50, 640, 136),
 ])
 def test_dgemm_matches_numpy(ctx, ta, tb, m, n, k):
     rng = np.random.default_rng(m * 7 + n * 3 + k)
