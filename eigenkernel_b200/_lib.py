@@ -75,6 +75,17 @@ _SIGS = {
     "ekb200_profile_rows": [c_void_p],
     "ekb200_profile_row": [c_void_p, c_int, POINTER(c_char_p), POINTER(c_int), POINTER(c_double), POINTER(c_double),
                            POINTER(c_int64)],
+    "ekb200_eval_residual_norm": [c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p,
+                                  c_void_p, c_void_p, c_void_p, c_int64, POINTER(c_double), POINTER(c_double),
+                                  POINTER(c_double)],
+    "ekb200_eval_orthogonality": [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
+                                  c_int64, POINTER(c_double)],
+    "ekb200_get_ipratios": [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p],
+    "ekb200_eval_residual_norm_dev": [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
+                                      c_void_p, c_int64, POINTER(c_double), POINTER(c_double), POINTER(c_double)],
+    "ekb200_eval_orthogonality_dev": [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64,
+                                      POINTER(c_double)],
+    "ekb200_get_ipratios_dev": [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p],
     "ekb200_comm_unique_id": [c_void_p],
     "ekb200_comm_init": [c_void_p, c_int, c_int, c_void_p],
     "ekb200_comm_info": [c_void_p, POINTER(c_int), POINTER(c_int)],

@@ -236,11 +236,3 @@ def log_json_text(setting: dict, events: list) -> str:
     out.append("  ]")
     out.append("}")
     return "\n".join(out) + "\n"
-
-
-# ------------------------------------------------------------------------------------------ IPR (host formula)
-def ipratios_host(X: np.ndarray, B: np.ndarray | None = None) -> np.ndarray:
-    """get_ipratios (distribute_matrix.f90:18-78) evaluated on the host:
-    sum_i v_ij^4 / (sum_i v_ij (B v)_ij)^2 (generalized) or / (sum_i v_ij^2)^2 (standard)."""
-    SV = X if B is None else B @ X
-    return (X ** 4).sum(axis=0) / ((X * SV).sum(axis=0) ** 2)

@@ -573,6 +573,130 @@ int ekb200_sygvd_coo(ekb200_ctx* h, int64_t n, int64_t nev, int64_t nnzA, const 
   return solve_host(h, n, nev, nullptr, 0, &a, nnzB > 0, nullptr, 0, nnzB > 0 ? &b : nullptr, w, Z, ldz);
 }
 
+// ---- acceptance metrics and IPRs (verify.cu)
+int ekb200_eval_residual_norm_dev(ekb200_ctx* h, int64_t n, int64_t ncheck, const double* A, int64_t lda, const double* B,
+                                  int64_t ldb, const double* w, const double* X, int64_t ldx, double* A_norm,
+                                  double* res_norm_ave, double* res_norm_max) {
+  CHECK_CTX(h);
+  if (n <= 0) return -2;
+  if (ncheck <= 0 || ncheck > n) return -3;
+  if (!A) return -4;
+  if (lda < n) return -5;
+  if (B && ldb < n) return -7;
+  if (!w) return -8;
+  if (!X) return -9;
+  if (ldx < n) return -10;
+  return eval_residual_norm(ctx, n, ncheck, A, lda, B, ldb, w, X, ldx, A_norm, res_norm_ave, res_norm_max);
+}
+int ekb200_eval_orthogonality_dev(ekb200_ctx* h, int64_t n, int64_t index1, int64_t index2, const double* X, int64_t ldx,
+                                  const double* B, int64_t ldb, double* orthogonality) {
+  CHECK_CTX(h);
+  if (n <= 0) return -2;
+  if (index1 < 1) return -3;
+  if (index2 < index1 || index2 > n) return -4;
+  if (!X) return -5;
+  if (ldx < n) return -6;
+  if (B && ldb < n) return -8;
+  return eval_orthogonality(ctx, n, index1, index2, X, ldx, B, ldb, orthogonality);
+}
+int ekb200_get_ipratios_dev(ekb200_ctx* h, int64_t n, int64_t nvec, const double* X, int64_t ldx, const double* B,
+                            int64_t ldb, double* ipratios) {
+  CHECK_CTX(h);
+  if (n <= 0) return -2;
+  if (nvec <= 0 || nvec > n) return -3;
+  if (!X) return -4;
+  if (ldx < n) return -5;
+  if (B && ldb < n) return -7;
+  if (!ipratios) return -8;
+  return get_ipratios(ctx, n, nvec, X, ldx, B, ldb, ipratios);
+}
+
+// Host-side eigenpairs + replicated COO matrices, as the reference routines receive them.  `what`: 0 residual,
+// 1 orthogonality, 2 IPR.  X is the rank's LOCAL piece (n x nloc of the nvec eigenvector columns).
+static int verify_host(ekb200_ctx* h, int what, int64_t n, int64_t nvec, int64_t a1, int64_t a2, int64_t nnzA,
+                       const int32_t* ijA, const double* vA, int64_t nnzB, const int32_t* ijB, const double* vB,
+                       const double* w, const double* X, int64_t ldx, double* o1, double* o2, double* o3) {
+  Ctx* ctx = &h->c;
+  const i64 ld = round_up(n, 8);
+  double *dA = nullptr, *dB = nullptr, *dX = nullptr, *dw = nullptr;
+  auto cleanup = [&]() {
+    cudaStreamSynchronize(ctx->stream);
+    ctx_free(ctx, dA); ctx_free(ctx, dB); ctx_free(ctx, dX); ctx_free(ctx, dw);
+  };
+  int rc = 0;
+  if (what == 0) rc = ctx_alloc(ctx, (void**)&dA, (size_t)ld * n * 8);
+  if (!rc && nnzB > 0) rc = ctx_alloc(ctx, (void**)&dB, (size_t)ld * n * 8);
+  if (!rc) rc = ctx_alloc(ctx, (void**)&dX, (size_t)ld * nvec * 8);
+  if (!rc && what == 0) rc = ctx_alloc(ctx, (void**)&dw, (size_t)(n + 8) * 8);
+  if (!rc && what == 0) rc = ekb200_coo_to_dense(h, n, nnzA, ijA, vA, dA, ld);
+  if (!rc && nnzB > 0) rc = ekb200_coo_to_dense(h, n, nnzB, ijB, vB, dB, ld);
+  if (!rc) {
+    std::vector<i64> zb;
+    slab_bounds(nvec, ctx->nranks, 128, zb);
+    const i64 c0 = zb[ctx->rank], kc = zb[ctx->rank + 1] - zb[ctx->rank];
+    cudaError_t ce = cudaSuccess;
+    if (kc > 0)
+      ce = cudaMemcpy2DAsync(dX + c0 * ld, ld * 8, X, ldx * 8, n * 8, kc, cudaMemcpyHostToDevice, ctx->stream);
+    if (ce == cudaSuccess && what == 0)
+      ce = cudaMemcpyAsync(dw, w, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream);
+    if (ce != cudaSuccess) {
+      ctx->last_cuda = ce;
+      ctx->last_error = std::string("h2d: ") + cudaGetErrorString(ce);
+      rc = EKB_ERR_CUDA;
+    }
+    // the checked columns need not coincide with the rank's slab of the nvec computed ones: make X whole
+    if (!rc && ctx->nranks > 1) rc = comm_allgather_cols(ctx, dX, ld, zb);
+  }
+  if (!rc) {
+    if (what == 0) rc = eval_residual_norm(ctx, n, a1, dA, ld, dB, ld, dw, dX, ld, o1, o2, o3);
+    else if (what == 1) rc = eval_orthogonality(ctx, n, a1, a2, dX, ld, dB, ld, o1);
+    else rc = get_ipratios(ctx, n, nvec, dX, ld, dB, ld, o1);
+  }
+  cleanup();
+  return rc;
+}
+
+int ekb200_eval_residual_norm(ekb200_ctx* h, int64_t n, int64_t nvec, int64_t ncheck, int64_t nnzA, const int32_t* ijA,
+                              const double* vA, int64_t nnzB, const int32_t* ijB, const double* vB, const double* w,
+                              const double* X, int64_t ldx, double* A_norm, double* res_norm_ave, double* res_norm_max) {
+  CHECK_CTX(h);
+  if (n <= 0) return -2;
+  if (nvec <= 0 || nvec > n) return -3;
+  if (ncheck <= 0 || ncheck > nvec) return -4;
+  if (nnzA < 0 || (nnzA > 0 && (!ijA || !vA))) return -5;
+  if (nnzB < 0 || (nnzB > 0 && (!ijB || !vB))) return -8;
+  if (!w) return -11;
+  if (!X) return -12;
+  if (ldx < n) return -13;
+  return verify_host(h, 0, n, nvec, ncheck, 0, nnzA, ijA, vA, nnzB, ijB, vB, w, X, ldx, A_norm, res_norm_ave,
+                     res_norm_max);
+}
+int ekb200_eval_orthogonality(ekb200_ctx* h, int64_t n, int64_t nvec, int64_t index1, int64_t index2, int64_t nnzB,
+                              const int32_t* ijB, const double* vB, const double* X, int64_t ldx,
+                              double* orthogonality) {
+  CHECK_CTX(h);
+  if (n <= 0) return -2;
+  if (nvec <= 0 || nvec > n) return -3;
+  if (index1 < 1) return -4;
+  if (index2 < index1 || index2 > nvec) return -5;
+  if (nnzB < 0 || (nnzB > 0 && (!ijB || !vB))) return -6;
+  if (!X) return -9;
+  if (ldx < n) return -10;
+  return verify_host(h, 1, n, nvec, index1, index2, 0, nullptr, nullptr, nnzB, ijB, vB, nullptr, X, ldx, orthogonality,
+                     nullptr, nullptr);
+}
+int ekb200_get_ipratios(ekb200_ctx* h, int64_t n, int64_t nvec, int64_t nnzB, const int32_t* ijB, const double* vB,
+                        const double* X, int64_t ldx, double* ipratios) {
+  CHECK_CTX(h);
+  if (n <= 0) return -2;
+  if (nvec <= 0 || nvec > n) return -3;
+  if (nnzB < 0 || (nnzB > 0 && (!ijB || !vB))) return -4;
+  if (!X) return -7;
+  if (ldx < n) return -8;
+  if (!ipratios) return -9;
+  return verify_host(h, 2, n, nvec, 0, 0, 0, nullptr, nullptr, nnzB, ijB, vB, nullptr, X, ldx, ipratios, nullptr, nullptr);
+}
+
 // ---- multi-GPU: one context per rank (dist.cu)
 int ekb200_comm_unique_id(void* id128) {
   if (!id128) return -1;

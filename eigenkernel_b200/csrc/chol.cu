@@ -208,19 +208,78 @@ static int potrf_rec(Ctx* ctx, i64 n, double* A, i64 lda, double* invd, i64 goff
   return potrf_rec(ctx, n2, A22, lda, invd + (n1 / NB) * NB * NB, goff + n1, tmp);
 }
 
+// Sharded recursion (P > 1 ranks, every rank holds the same A): at every level of at least POTRF_DIST_MIN
+// columns the two GEMM-shaped steps are dealt to the ranks --
+//   A21 <- A21 L11^-T   by ROW slabs of A21 (each rank solves for its rows), then an all-gather;
+//   A22 -= A21 A21^T    by COLUMN slabs of the lower triangle (boundaries chosen for equal area), then an all-gather;
+// -- while the small diagonal sub-problems stay replicated (deterministic kernels: identical bits on every rank).
+// This is pdpotrf's panel broadcast + trailing update with the process grid folded onto the GPUs of the box.
+constexpr i64 POTRF_DIST_MIN = 2048;
+
+static int potrf_dist_rec(Ctx* ctx, i64 n, double* A, i64 lda, double* invd, i64 goff, double* tmp, double* pack) {
+  if (ctx->nranks <= 1 || n < POTRF_DIST_MIN) return potrf_rec(ctx, n, A, lda, invd, goff, tmp);
+  const int P = ctx->nranks, r = ctx->rank;
+  const i64 nblk = (n + NB - 1) / NB;
+  const i64 n1 = ((nblk + 1) / 2) * NB, n2 = n - n1;
+  double* A21 = A + n1;
+  double* A22 = A + n1 * lda + n1;
+  EKB_TRY(potrf_dist_rec(ctx, n1, A, lda, invd, goff, tmp, pack));
+  {  // row slabs of A21
+    std::vector<i64> rb;
+    slab_bounds(n2, P, NB, rb);
+    const i64 chunk = rb[1] - rb[0];  // the largest slab (slab 0)
+    const i64 r0 = rb[r], nr = rb[r + 1] - rb[r];
+    if (nr > 0) {
+      EKB_TRY(trsm_rec(ctx, TRSM_RLT, nr, n1, A, lda, invd, A21 + r0, lda, tmp));
+      EKB_TRY(copy_matrix(ctx, A21 + r0, lda, pack + (size_t)r * chunk * n1, chunk, nr, n1));
+    }
+    EKB_TRY(comm_allgather(ctx, pack + (size_t)r * chunk * n1, pack, (size_t)chunk * n1));
+    for (int q = 0; q < P; ++q) {
+      const i64 q0 = rb[q], nq = rb[q + 1] - rb[q];
+      if (q != r && nq > 0) EKB_TRY(copy_matrix(ctx, pack + (size_t)q * chunk * n1, chunk, A21 + q0, lda, nq, n1));
+    }
+  }
+  {  // column slabs of the lower triangle of A22, equal areas: c_q = n2 (1 - sqrt(1 - q / P))
+    std::vector<i64> cb(P + 1, 0);
+    for (int q = 1; q < P; ++q) {
+      i64 c = (i64)((double)n2 * (1.0 - sqrt(1.0 - (double)q / P)));
+      c = c / NB * NB;
+      cb[q] = c < cb[q - 1] ? cb[q - 1] : (c > n2 ? n2 : c);
+    }
+    cb[P] = n2;
+    const i64 c0 = cb[r], nc = cb[r + 1] - cb[r];
+    if (nc > 0) {
+      GemmP p;
+      p.m = (int)(n2 - c0); p.n = (int)nc; p.k = (int)n1;
+      p.A = A21 + c0; p.lda = lda; p.B = A21 + c0; p.ldb = lda; p.C = A22 + c0 * lda + c0; p.ldc = lda;
+      p.alpha = -1.0; p.beta = 1.0;
+      EKB_TRY(gemm(ctx, GEMM_TB, p, /*tri_keep=*/1));
+    }
+    EKB_TRY(comm_allgather_cols(ctx, A22, lda, cb));
+  }
+  return potrf_dist_rec(ctx, n2, A22, lda, invd + (n1 / NB) * NB * NB, goff + n1, tmp, pack);
+}
+
 int potrf_lower(Ctx* ctx, i64 n, double* B, i64 ldb, double* invd) {
   if (n <= 0) return 0;
-  double* tmp = nullptr;
+  double *tmp = nullptr, *pack = nullptr;
   EKB_TRY(ctx_alloc(ctx, (void**)&tmp, (size_t)round_up(n, 2) * NB * sizeof(double)));
+  if (ctx->nranks > 1 && n >= POTRF_DIST_MIN) {
+    const i64 h = (((n + NB - 1) / NB + 1) / 2) * NB;  // largest n1; n2 <= n1
+    const size_t pack_doubles = (size_t)(h + (i64)NB * ctx->nranks) * h;
+    int rc = ctx_alloc(ctx, (void**)&pack, pack_doubles * sizeof(double));
+    if (rc) { ctx_free(ctx, tmp); return rc; }
+  }
   *ctx->h_info = 0x7fffffff;
   EKB_CUDA(cudaMemcpyAsync(ctx->d_info, ctx->h_info, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-  int rc = potrf_rec(ctx, n, B, ldb, invd, 0, tmp);
+  int rc = potrf_dist_rec(ctx, n, B, ldb, invd, 0, tmp, pack);
   if (rc == 0) {
     EKB_CUDA(cudaMemcpyAsync(ctx->h_info, ctx->d_info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     EKB_CUDA(cudaStreamSynchronize(ctx->stream));
     if (*ctx->h_info != 0x7fffffff) rc = *ctx->h_info;
   }
   ctx_free(ctx, tmp);
+  if (pack) ctx_free(ctx, pack);
   return rc;
 }
 

@@ -185,4 +185,11 @@ int sy2sb_dist(Ctx* ctx, i64 n, int b, double* A, i64 lda, double* AB, i64 ldab,
 int transpose_matrix(Ctx* ctx, const double* A, i64 lda, i64 m, i64 n, double* B, i64 ldb);
 int sygst_dist(Ctx* ctx, i64 n, double* A, i64 lda, const double* L, i64 ldl, const double* invd);
 
+// ---------------------------------------------------------------- acceptance metrics + IPR (verify.cu)
+int eval_residual_norm(Ctx* ctx, i64 n, i64 ncheck, const double* A, i64 lda, const double* B, i64 ldb, const double* w,
+                       const double* Xfull, i64 ldx, double* A_norm, double* res_ave, double* res_max);
+int eval_orthogonality(Ctx* ctx, i64 n, i64 index1, i64 index2, const double* Xfull, i64 ldx, const double* B, i64 ldb,
+                       double* orthogonality);
+int get_ipratios(Ctx* ctx, i64 n, i64 nvec, const double* Xfull, i64 ldx, const double* B, i64 ldb, double* ipr);
+
 }  // namespace ekb

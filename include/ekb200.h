@@ -156,6 +156,36 @@ int ekb200_profile_rows(const ekb200_ctx* ctx);
 int ekb200_profile_row(const ekb200_ctx* ctx, int i, const char** stage, int* family, double* seconds, double* work,
                        int64_t* launches);
 
+/* ---- acceptance metrics and IPRs on the device.
+ * ekb200_eval_residual_norm  = eval_residual_norm_blacs (src/verifier.f90:75-204, option -c):
+ *     A_norm = ||A||_F, res_norm_ave / res_norm_max = mean / max over the first ncheck columns of
+ *     ||A x_j - lambda_j B x_j||_2 / ||A||_F  (no division by ||x_j||, exactly as verifier.f90:198-199).
+ * ekb200_eval_orthogonality  = eval_orthogonality_blacs (src/verifier.f90:233-330, option -t): Frobenius norm of the
+ *     Gram matrix X(:, index1:index2)^T B X(:, index1:index2) scaled to unit diagonal with the diagonal zeroed
+ *     (index1/index2 1-based, inclusive).
+ * ekb200_get_ipratios        = get_ipratios (src/distribute_matrix.f90:18-78, ipratios.dat): sum_i x_ij^4 /
+ *     (sum_i x_ij (B x)_ij)^2 for the first nvec columns, B = I for the standard problem.
+ * Host variants take what the reference routines take: the replicated COO matrices (ij = Fortran suffix(2,nnz),
+ * 1-based; nnzB = 0: standard problem) and the eigenpairs -- w(n) and X, the rank's LOCAL piece (n x nloc of the
+ * nvec computed eigenvector columns; all of them on one rank).  *_dev variants work on device-resident full
+ * symmetric A / B and on the n x nvec eigenvector buffer of the *_dev solvers (residual and IPR read the rank's own
+ * slab of the checked columns, orthogonality needs all of index1..index2: call ekb200_comm_allgather_slabs first
+ * when there is more than one rank).  Results are returned on the host, identical on every rank. */
+int ekb200_eval_residual_norm(ekb200_ctx* ctx, int64_t n, int64_t nvec, int64_t ncheck, int64_t nnzA, const int32_t* ijA,
+                              const double* vA, int64_t nnzB, const int32_t* ijB, const double* vB, const double* w,
+                              const double* X, int64_t ldx, double* A_norm, double* res_norm_ave, double* res_norm_max);
+int ekb200_eval_orthogonality(ekb200_ctx* ctx, int64_t n, int64_t nvec, int64_t index1, int64_t index2, int64_t nnzB,
+                              const int32_t* ijB, const double* vB, const double* X, int64_t ldx, double* orthogonality);
+int ekb200_get_ipratios(ekb200_ctx* ctx, int64_t n, int64_t nvec, int64_t nnzB, const int32_t* ijB, const double* vB,
+                        const double* X, int64_t ldx, double* ipratios);
+int ekb200_eval_residual_norm_dev(ekb200_ctx* ctx, int64_t n, int64_t ncheck, const double* dev_A, int64_t lda,
+                                  const double* dev_B, int64_t ldb, const double* dev_w, const double* dev_X, int64_t ldx,
+                                  double* A_norm, double* res_norm_ave, double* res_norm_max);
+int ekb200_eval_orthogonality_dev(ekb200_ctx* ctx, int64_t n, int64_t index1, int64_t index2, const double* dev_X,
+                                  int64_t ldx, const double* dev_B, int64_t ldb, double* orthogonality);
+int ekb200_get_ipratios_dev(ekb200_ctx* ctx, int64_t n, int64_t nvec, const double* dev_X, int64_t ldx,
+                            const double* dev_B, int64_t ldb, double* ipratios);
+
 /* ---- multi-GPU: ONE CONTEXT PER RANK, one rank per B200 (replaces the BLACS grid of src/processes.f90:17-65 and
  * the block-cyclic scatter of src/distribute_matrix.f90:92-148).  Rank 0 obtains a 128-byte id with
  * ekb200_comm_unique_id and hands it to the other ranks by whatever the host has (mpi_bcast in the Fortran app,

@@ -94,6 +94,21 @@ def main():
         assert np.array_equal(wl, w), "host and device entry points disagree on eigenvalues"
         if kc > 0:
             assert np.array_equal(Xl[:, :kc], X[:, c0:c0 + kc]), "local piece != slab of the device result"
+        # device-side checks through the host entry points: replicated COO in, local piece of X in
+        i, j = np.tril_indices(n)
+        ij = np.ascontiguousarray(np.stack([i + 1, j + 1], axis=1).astype(np.int32))
+        vA, vB = np.ascontiguousarray(A[i, j]), np.ascontiguousarray(B[i, j])
+        nnz = len(i)
+        an, ave, mx, orth = (ctypes.c_double() for _ in range(4))
+        ipr = np.zeros(nev)
+        nnzB = nnz if gen else 0
+        ctx.call("ekb200_eval_residual_norm", n, nev, nev, nnz, ij.ctypes.data, vA.ctypes.data, nnzB,
+                 ij.ctypes.data if gen else None, vB.ctypes.data if gen else None, wl.ctypes.data, Xl.ctypes.data, n,
+                 ctypes.byref(an), ctypes.byref(ave), ctypes.byref(mx))
+        ctx.call("ekb200_eval_orthogonality", n, nev, 1, nev, nnzB, ij.ctypes.data if gen else None,
+                 vB.ctypes.data if gen else None, Xl.ctypes.data, n, ctypes.byref(orth))
+        ctx.call("ekb200_get_ipratios", n, nev, nnzB, ij.ctypes.data if gen else None, vB.ctypes.data if gen else None,
+                 Xl.ctypes.data, n, ipr.ctypes.data)
         full = ekdist.gather_columns(Xl[:, :kc], nev)
         if rank == 0:
             assert np.array_equal(full, X)
@@ -110,6 +125,11 @@ def main():
             print(f"[dist_check] P={world} n={n} nev={nev} gen={gen}: res={r['res_max_over_A']:.2e} "
                   f"orth={o['orth_fro']:.2e} dlambda_vs_1gpu={dw_rel:.2e} collectives="
                   f"{ctx.lib.ekb200_num_collectives(ctx.h)}", flush=True)
+            vo = lt.orthogonality_metrics(X, Bm)["verifier_orthogonality"]
+            assert abs(mx.value - r["res_max_over_A"]) <= 1e-6 * r["res_max_over_A"] + 1e-18, (mx.value, r)
+            assert abs(ave.value - r["res_avg_over_A"]) <= 1e-6 * r["res_avg_over_A"] + 1e-18
+            assert abs(orth.value - vo) <= 1e-6 * vo + 1e-18, (orth.value, vo)
+            assert np.max(np.abs(ipr - lt.ipratios(X, Bm)) / lt.ipratios(X, Bm)) <= 1e-10
             assert r["res_max_over_A"] <= 1e-12 * n, r
             assert o["orth_fro"] <= 1e-12 * n, o
             assert dw_rel <= 1e-12

@@ -9,7 +9,7 @@ import os
 import numpy as np
 import pytest
 
-from eigenkernel_b200 import app_io
+from eigenkernel_b200 import app_io, verifier
 from eigenkernel_b200.solver import Argument, eigen_solver, validate_argument
 from oracle import lapack_twin as lt
 
@@ -63,7 +63,7 @@ def test_bnz30_general_b200_matches_shipped_answers(ctx, golden_dir):
     A, B = app_io.sparse_to_dense(mA), app_io.sparse_to_dense(mB)
     check_pairs(A, B, w, ep.blacs.Vectors, ev)
     ipr_ref = app_io.read_indexed_values(os.path.join(golden_dir, "ELSES_MATRIX_BNZ30_ipr.txt"))
-    ipr = app_io.ipratios_host(ep.blacs.Vectors, B)
+    ipr = verifier.get_ipratios(proc, ep.blacs.Vectors, ep.blacs.desc, mB, ctx=ctx)
     # near-degenerate pairs (gaps 3e-9..2e-7) limit reproducibility of the IPRs
     assert np.max(np.abs(ipr - ipr_ref) / ipr_ref) <= 1e-6
     # the eigenvalues.dat text of well-separated eigenvalues agrees with the shipped file to 13 digits
