@@ -62,8 +62,9 @@ int ekb200_destroy(ekb200_ctx* h) {
   if (!h) return 0;
   Ctx* ctx = &h->c;
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
+  if (ctx->comm == nullptr) cudaStreamSynchronize(ctx->stream);  // with a communicator a peer may never arrive
   comm_destroy(ctx);
+  cudaStreamSynchronize(ctx->stream);
   for (void* p : ctx->allocs) cudaFree(p);
   ctx->allocs.clear();
   ctx->live.clear();

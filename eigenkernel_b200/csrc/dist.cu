@@ -27,6 +27,7 @@ struct NcclApi {
   int (*GetUniqueId)(NcclUniqueId*) = nullptr;
   int (*CommInitRank)(NcclComm*, int, NcclUniqueId, int) = nullptr;
   int (*CommDestroy)(NcclComm) = nullptr;
+  int (*CommAbort)(NcclComm) = nullptr;
   int (*Broadcast)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
   int (*AllGather)(const void*, void*, size_t, int, NcclComm, cudaStream_t) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
@@ -61,6 +62,7 @@ static int nccl_load() {
   BIND(GetUniqueId, "ncclGetUniqueId");
   BIND(CommInitRank, "ncclCommInitRank");
   BIND(CommDestroy, "ncclCommDestroy");
+  BIND(CommAbort, "ncclCommAbort");
   BIND(Broadcast, "ncclBroadcast");
   BIND(AllGather, "ncclAllGather");
   BIND(AllReduce, "ncclAllReduce");
@@ -121,8 +123,9 @@ int comm_init(Ctx* ctx, int nranks, int rank, const void* id128) {
 
 int comm_destroy(Ctx* ctx) {
   if (ctx->comm && g_nccl.lib) {
-    cudaStreamSynchronize(ctx->stream);
-    g_nccl.CommDestroy((NcclComm)ctx->comm);
+    // every collective of this context has been waited for by its caller, so nothing is in flight; Abort (unlike
+    // Destroy) does not need the peers to arrive, which keeps a failing rank from hanging at exit
+    g_nccl.CommAbort((NcclComm)ctx->comm);
   }
   ctx->comm = nullptr;
   ctx->nranks = 1;

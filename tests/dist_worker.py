@@ -22,6 +22,9 @@ sys.path.insert(0, ROOT)
 
 
 def main():
+    # a hung collective must not burn GPU time: dump every thread's stack and exit after the deadline
+    import faulthandler
+    faulthandler.dump_traceback_later(float(os.environ.get("EKB200_TEST_DEADLINE", "240")), exit=True)
     import torch
     import torch.distributed as dist
 
@@ -51,6 +54,8 @@ def main():
         cases += [(4096, 4096, True, 16), (8192, 8192, True, 20240601)]
     done = 0
     for n, nev, gen, seed in cases:
+        if rank == 0:
+            print(f"[dist_check] case n={n} nev={nev} gen={gen}", flush=True)
         ld = (n + 7) // 8 * 8
         c0, kc = ekdist.local_slab(nev, world, rank)
         cc0, ckc = ctypes.c_int64(), ctypes.c_int64()
@@ -94,7 +99,9 @@ def main():
         assert np.array_equal(wl, w), "host and device entry points disagree on eigenvalues"
         if kc > 0:
             assert np.array_equal(Xl[:, :kc], X[:, c0:c0 + kc]), "local piece != slab of the device result"
-        # device-side checks through the host entry points: replicated COO in, local piece of X in
+        # device-side checks through the host entry points: replicated COO in, local piece of X in (perturbed, so
+        # that the metrics are well above rounding noise and can be compared tightly)
+        Xl = np.asfortranarray(Xl + 1e-9 * np.random.default_rng(1000 + rank).standard_normal(Xl.shape))
         i, j = np.tril_indices(n)
         ij = np.ascontiguousarray(np.stack([i + 1, j + 1], axis=1).astype(np.int32))
         vA, vB = np.ascontiguousarray(A[i, j]), np.ascontiguousarray(B[i, j])
@@ -111,7 +118,7 @@ def main():
                  Xl.ctypes.data, n, ipr.ctypes.data)
         full = ekdist.gather_columns(Xl[:, :kc], nev)
         if rank == 0:
-            assert np.array_equal(full, X)
+            assert np.max(np.abs(full - X)) <= 1e-8
             dA, dB, dZ1, dw1 = solve(solo)
             w1 = np.zeros(n)
             solo.call("ekb200_d2h", w1.ctypes.data, dw1, n * 8)
@@ -125,11 +132,13 @@ def main():
             print(f"[dist_check] P={world} n={n} nev={nev} gen={gen}: res={r['res_max_over_A']:.2e} "
                   f"orth={o['orth_fro']:.2e} dlambda_vs_1gpu={dw_rel:.2e} collectives="
                   f"{ctx.lib.ekb200_num_collectives(ctx.h)}", flush=True)
-            vo = lt.orthogonality_metrics(X, Bm)["verifier_orthogonality"]
-            assert abs(mx.value - r["res_max_over_A"]) <= 1e-6 * r["res_max_over_A"] + 1e-18, (mx.value, r)
-            assert abs(ave.value - r["res_avg_over_A"]) <= 1e-6 * r["res_avg_over_A"] + 1e-18
-            assert abs(orth.value - vo) <= 1e-6 * vo + 1e-18, (orth.value, vo)
-            assert np.max(np.abs(ipr - lt.ipratios(X, Bm)) / lt.ipratios(X, Bm)) <= 1e-10
+            rp = lt.residual_metrics(A, w[:nev], full, Bm)
+            vo = lt.orthogonality_metrics(full, Bm)["verifier_orthogonality"]
+            assert abs(an.value - rp["A_norm"]) <= 1e-13 * rp["A_norm"]
+            assert abs(mx.value - rp["res_max_over_A"]) <= 1e-5 * rp["res_max_over_A"], (mx.value, rp)
+            assert abs(ave.value - rp["res_avg_over_A"]) <= 1e-5 * rp["res_avg_over_A"]
+            assert abs(orth.value - vo) <= 1e-5 * vo, (orth.value, vo)
+            assert np.max(np.abs(ipr - lt.ipratios(full, Bm)) / lt.ipratios(full, Bm)) <= 1e-10
             assert r["res_max_over_A"] <= 1e-12 * n, r
             assert o["orth_fro"] <= 1e-12 * n, o
             assert dw_rel <= 1e-12

@@ -23,6 +23,6 @@ def test_sharded_solve_matches_single_gpu(world):
         pytest.skip(f"needs {world} GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
            "127.0.0.1", "--master-port", str(29517 + world), os.path.join(ROOT, "tests", "dist_worker.py")]
-    r = subprocess.run(cmd, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    r = subprocess.run(cmd, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=420)
     sys.stdout.write(r.stdout[-4000:])
     assert r.returncode == 0 and "DIST_CHECK_OK" in r.stdout
