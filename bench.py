@@ -335,8 +335,8 @@ def run_ours(args) -> None:
     for name, s in stage.items():
         ent = {"seconds": s}
         if name in can and s > 0:
-            ent["tflops"] = can[name] / s / 1e12
-            ent["frac_of_fp64_peak"] = ent["tflops"] / peak["dmma_tflops"]
+            ent["tflops"] = can[name] / s / 1e12  # canonical FLOPs of the whole stage / this rank's stage seconds
+            ent["frac_of_fp64_peak"] = ent["tflops"] / (peak["dmma_tflops"] * world)  # of the aggregate peak
         if name == "eigen_solver_b200:sb2st" and s > 0:
             band = lib.ekb200_get_band(h)
             ent["gbs_effective"] = 12.0 * band * n * n / s / 1e9

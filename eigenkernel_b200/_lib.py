@@ -26,6 +26,7 @@ _lib = None
 # name -> (argtypes)  ; every function returns int info unless listed in _RESTYPE
 _SIGS = {
     "ekb200_version": [],
+    "ekb200_device_count": [],
     "ekb200_create": [POINTER(c_void_p), c_int],
     "ekb200_destroy": [c_void_p],
     "ekb200_strerror": [c_int],

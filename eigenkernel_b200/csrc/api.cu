@@ -36,7 +36,16 @@ static int ensure_invd(ekb200_ctx* h, i64 n) {
 
 extern "C" {
 
-int ekb200_version(void) { return 100; }
+int ekb200_version(void) { return 110; }
+
+int ekb200_device_count(void) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return ndev;
+}
 
 int ekb200_create(ekb200_ctx** out, int device) {
   if (!out) return -1;

@@ -25,21 +25,24 @@ __device__ __forceinline__ void bar_named(int id, int count) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 
-// 4 B threads per CTA, split into four groups of B threads (whole warps) that work on the three blocks of the
-// window CONCURRENTLY once the reflector is known:
-//   group 0: left-apply H on the L block and stream it back (final for this sweep);
-//   group 1: two-sided update of the diagonal block D (p = tau D v, w = p - tau/2 (p.v) v), then -- together with
-//   group 3 -- D -= v w^T + w v^T written straight back to the band (even / odd columns);
-//   group 2: right-apply on the B block (u = tau B v, B -= u v^T), which becomes the L block of the next task.
-// All global loads of a task (D and B blocks, 2 * B/4 independent loads per thread) are issued before the first
-// use, so a task pays ONE L2 round trip instead of 2 B dependent ones; the reflector itself is formed by a
-// single warp (shuffle reduction, no block barrier).
+// 4 B threads per CTA in four groups of B threads (whole warps).  A task's work is arranged around its ONE
+// dependency on the previous sweep (the D and B blocks of the band):
+//   group 0 needs nothing from the previous sweep (for t >= 1 the L block is already in shared memory): warp 0 forms
+//   the reflector, then the group left-applies it to the L block and streams the block back -- all of this overlaps
+//   the dependency wait and the band loads of the other groups;
+//   groups 1-3: one thread polls the predecessor's progress counter, then the three groups issue ALL loads of the
+//   D and B blocks before first use (one L2 round trip per task instead of 2 B dependent ones);
+//   after one block barrier: group 1 forms p = tau D v and w = p - tau/2 (p.v) v, then groups 0, 1, 3 apply
+//   D -= v w^T + w v^T straight back to the band (columns dealt mod 3) while group 2 right-applies the reflector to
+//   the B block (which becomes the L block of the next task).
+// Progress is published by thread 0 after the closing barrier with a single cumulative fence.
 template <int B>
-__global__ void __launch_bounds__(4 * B) sb2st_kernel(double* __restrict__ AB, i64 ldab, i64 n, double* __restrict__ V2,
-                                                      i64 ldv, double* __restrict__ TAU2, int ldtau, int* __restrict__ prog,
-                                                      double* __restrict__ d_out, double* __restrict__ e_out) {
+__global__ void __launch_bounds__(4 * B, 2) sb2st_kernel(double* __restrict__ AB, i64 ldab, i64 n, double* __restrict__ V2,
+                                                         i64 ldv, double* __restrict__ TAU2, int ldtau,
+                                                         int* __restrict__ prog, double* __restrict__ d_out,
+                                                         double* __restrict__ e_out) {
   constexpr int LDS = B + 1;
-  constexpr int CPT = B / 4;        // columns of D / B loaded per thread
+  constexpr int CPT = (B + 2) / 3;  // columns of D / B loaded per thread of groups 1-3
   constexpr int EPL = B / 32;       // reflector elements per lane of warp 0
   constexpr int WPG = B / 32;       // warps per group
   extern __shared__ double sm[];
@@ -63,79 +66,61 @@ __global__ void __launch_bounds__(4 * B) sb2st_kernel(double* __restrict__ AB, i
       const i64 r0 = s + 1 + (i64)t * B;
       const int nr = (int)min((i64)B, n - r0);               // rows of R (>= 2)
       const int nr2 = (int)max((i64)0, min((i64)B, n - (r0 + B)));  // rows of the block below
-      // ---- wait for sweep s-1
-      if (s > 0) {
-        if (tid == 0) {
-          const int need = t + 3;
-          while (ld_volatile(prog + (s - 1)) < need) { __nanosleep(20); }
-          __threadfence();
-        }
-        __syncthreads();
-      }
-      // ---- load: every thread issues its 2 * CPT independent loads, then stores them to shared memory
-      {
-        double xd[CPT], xb[CPT];
-#pragma unroll
-        for (int q = 0; q < CPT; ++q) {
-          const int jj = grp + 4 * q;
-          const double* col = AB + (r0 + jj) * ldab;
-          xd[q] = (jj < nr && li >= jj && li < nr) ? __ldcg(col + (li - jj)) : 0.0;
-          xb[q] = (jj < nr && li < nr2) ? __ldcg(col + (B + li - jj)) : 0.0;
-        }
-        if (t == 0 && grp == 0 && li < nr) bufL[li] = __ldcg(AB + s * ldab + 1 + li);  // L block = column s
-#pragma unroll
-        for (int q = 0; q < CPT; ++q) {
-          const int jj = grp + 4 * q;
-          if (jj < nr && li >= jj && li < nr) {  // D block: A(R,R), lower stored; mirrored into full
-            bufD[jj * LDS + li] = xd[q];
-            bufD[li * LDS + jj] = xd[q];
+      const int need = t + 3;                                // tasks 0 .. t+2 of sweep s-1 must be complete
+      if (t == 0) {
+        // the L block is just column s of the band, which the previous sweep has modified: wait first
+        if (s > 0) {
+          if (tid == 0) {
+            while (ld_volatile(prog + (s - 1)) < need) {}
+            __threadfence();
           }
-          if (jj < nr && li < nr2) bufB[jj * LDS + li] = xb[q];  // B block: A(R+B, R)
+          __syncthreads();
         }
+        if (grp == 0 && li < nr) bufL[li] = __ldcg(AB + s * ldab + 1 + li);
       }
-      __syncthreads();
-      // ---- 1. reflector from x = bufL(0:nr, 0), by warp 0 alone
-      if (tid < 32) {
-        double xs[EPL];
-        double sq = 0.0;
-#pragma unroll
-        for (int q = 0; q < EPL; ++q) {
-          const int e = lane + 32 * q;
-          xs[q] = (e > 0 && e < nr) ? bufL[e] : 0.0;
-          sq += xs[q] * xs[q];
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-        const double alpha = bufL[0];
-        double beta, tau, sc;
-        if (sq == 0.0) {
-          beta = alpha; tau = 0.0; sc = 0.0;
-        } else {
-          beta = -copysign(sqrt(alpha * alpha + sq), alpha);
-          tau = (beta - alpha) / beta;
-          sc = 1.0 / (alpha - beta);
-        }
-        __syncwarp();
-        if (lane == 0) {
-          s_tau = tau;
-          TAU2[(i64)s * ldtau + t] = tau;
-        }
-#pragma unroll
-        for (int q = 0; q < EPL; ++q) {
-          const int e = lane + 32 * q;
-          const double vi = (e == 0) ? 1.0 : (e < nr ? xs[q] * sc : 0.0);
-          v[e] = vi;
-          if (e < nr) {
-            V2[s * ldv + r0 + e] = vi;
-            bufL[e] = (e == 0) ? beta : 0.0;
-          }
-        }
-      }
-      __syncthreads();
-      const double tau = s_tau;
       if (grp == 0) {
+        if (t == 0) bar_named(1, B);
+        // ---- 1. reflector from x = bufL(0:nr, 0), by warp 0 alone
+        if (tid < 32) {
+          double xs[EPL];
+          double sq = 0.0;
+#pragma unroll
+          for (int q = 0; q < EPL; ++q) {
+            const int e = lane + 32 * q;
+            xs[q] = (e > 0 && e < nr) ? bufL[e] : 0.0;
+            sq += xs[q] * xs[q];
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+          const double alpha = bufL[0];
+          double beta, tau, sc;
+          if (sq == 0.0) {
+            beta = alpha; tau = 0.0; sc = 0.0;
+          } else {
+            beta = -copysign(sqrt(alpha * alpha + sq), alpha);
+            tau = (beta - alpha) / beta;
+            sc = 1.0 / (alpha - beta);
+          }
+          __syncwarp();
+          if (lane == 0) {
+            s_tau = tau;
+            TAU2[(i64)s * ldtau + t] = tau;
+          }
+#pragma unroll
+          for (int q = 0; q < EPL; ++q) {
+            const int e = lane + 32 * q;
+            const double vi = (e == 0) ? 1.0 : (e < nr ? xs[q] * sc : 0.0);
+            v[e] = vi;
+            if (e < nr) {
+              V2[s * ldv + r0 + e] = vi;
+              bufL[e] = (e == 0) ? beta : 0.0;
+            }
+          }
+        }
+        bar_named(1, B);
         // ---- 2. left-apply H to bufL(:, 1:B) (t >= 1), thread per column; then write the L block back
         if (t >= 1) {
+          const double tau = s_tau;
           const int jj = li;
           if (jj >= 1) {
             double dot = 0.0;
@@ -153,41 +138,37 @@ __global__ void __launch_bounds__(4 * B) sb2st_kernel(double* __restrict__ AB, i
         } else {
           if (li < nr) AB[s * ldab + 1 + li] = bufL[li];
         }
-      } else if (grp == 1) {
-        // ---- 3. two-sided on D: p = tau D v (thread per row), w = p - tau/2 (p.v) v
-        double pi = 0.0;
-        if (li < nr) {
-#pragma unroll 8
-          for (int jj = 0; jj < nr; ++jj) pi += bufD[jj * LDS + li] * v[jj];
-          pi *= tau;
-        }
-        const double vl = v[li];
-        double pv = (li < nr) ? pi * vl : 0.0;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) pv += __shfl_xor_sync(0xffffffffu, pv, o);
-        if (lane == 0) red[li >> 5] = pv;
-        bar_named(3, B);
-        double ptv = 0.0;
-#pragma unroll
-        for (int q = 0; q < WPG; ++q) ptv += red[q];
-        const double wi = (li < nr) ? pi - 0.5 * tau * ptv * vl : 0.0;
-        w[li] = wi;
-        bar_named(2, 2 * B);
-        // D -= v w^T + w v^T, even columns, lower part straight back to the band
-        if (li < nr) {
-#pragma unroll 4
-          for (int jj = 0; jj <= li; jj += 2)
-            AB[(r0 + jj) * ldab + (li - jj)] = bufD[jj * LDS + li] - vl * w[jj] - wi * v[jj];
-        }
-      } else if (grp == 3) {
-        bar_named(2, 2 * B);
-        if (li < nr) {
-          const double vl = v[li], wi = w[li];
-#pragma unroll 4
-          for (int jj = 1; jj <= li; jj += 2)
-            AB[(r0 + jj) * ldab + (li - jj)] = bufD[jj * LDS + li] - vl * w[jj] - wi * v[jj];
-        }
       } else {
+        // ---- wait for sweep s-1 (t >= 1; for t == 0 it happened above), then load the D and B blocks
+        if (t > 0 && s > 0) {
+          if (tid == B) {
+            while (ld_volatile(prog + (s - 1)) < need) {}
+            __threadfence();
+          }
+          bar_named(4, 3 * B);
+        }
+        double xd[CPT], xb[CPT];
+        const int g3 = grp - 1;
+#pragma unroll
+        for (int q = 0; q < CPT; ++q) {
+          const int jj = g3 + 3 * q;
+          const double* col = AB + (r0 + jj) * ldab;
+          xd[q] = (jj < nr && li >= jj && li < nr) ? __ldcg(col + (li - jj)) : 0.0;
+          xb[q] = (jj < nr && li < nr2) ? __ldcg(col + (B + li - jj)) : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < CPT; ++q) {
+          const int jj = g3 + 3 * q;
+          if (jj < nr && li >= jj && li < nr) {  // D block: A(R,R), lower stored; mirrored into full
+            bufD[jj * LDS + li] = xd[q];
+            bufD[li * LDS + jj] = xd[q];
+          }
+          if (jj < nr && li < nr2) bufB[jj * LDS + li] = xb[q];  // B block: A(R+B, R)
+        }
+      }
+      __syncthreads();
+      const double tau = s_tau;
+      if (grp == 2) {
         // ---- 4. right-apply on B: u = tau B v (thread per row), B -= u v^T
         if (li < nr2) {
           double u = 0.0;
@@ -202,11 +183,40 @@ __global__ void __launch_bounds__(4 * B) sb2st_kernel(double* __restrict__ AB, i
             for (int jj = 0; jj < nr; ++jj) AB[(r0 + jj) * ldab + (B + li - jj)] = bufB[jj * LDS + li];
           }
         }
+      } else {
+        // ---- 3. two-sided on D: p = tau D v (thread per row, group 1), w = p - tau/2 (p.v) v
+        const double vl = v[li];
+        if (grp == 1) {
+          double pi = 0.0;
+          if (li < nr) {
+#pragma unroll 8
+            for (int jj = 0; jj < nr; ++jj) pi += bufD[jj * LDS + li] * v[jj];
+            pi *= tau;
+          }
+          double pv = (li < nr) ? pi * vl : 0.0;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) pv += __shfl_xor_sync(0xffffffffu, pv, o);
+          if (lane == 0) red[li >> 5] = pv;
+          bar_named(3, B);
+          double ptv = 0.0;
+#pragma unroll
+          for (int q = 0; q < WPG; ++q) ptv += red[q];
+          w[li] = (li < nr) ? pi - 0.5 * tau * ptv * vl : 0.0;
+        }
+        bar_named(2, 3 * B);
+        // D -= v w^T + w v^T, lower part straight back to the band; columns dealt mod 3 to groups 0, 1, 3
+        if (li < nr) {
+          const double wi = w[li];
+          const int c0 = grp == 0 ? 0 : (grp == 1 ? 1 : 2);
+#pragma unroll 4
+          for (int jj = c0; jj <= li; jj += 3)
+            AB[(r0 + jj) * ldab + (li - jj)] = bufD[jj * LDS + li] - vl * w[jj] - wi * v[jj];
+        }
       }
-      // ---- publish progress
-      __threadfence();
+      // ---- publish progress: one barrier, then a single cumulative fence by the publishing thread
       __syncthreads();
       if (tid == 0) {
+        __threadfence();
         const int val = (t + 1 >= ntask) ? 0x3fffffff : (t + 1);
         *reinterpret_cast<volatile int*>(prog + s) = val;
       }

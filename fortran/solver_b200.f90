@@ -3,9 +3,20 @@
 ! hand-written CUDA.  House signature and error convention follow src/solver_scalapack_all.f90:127-168 and
 ! src/generalized_to_standard.f90:25-30; the dummy twin (solver_b200_dummy.f90) follows src/solver_elpa_dummy.f90.
 !
-! Deployment mode: one MPI rank (mpirun -np 1), GPUs selected by the library.  The BLACS grid is 1x1, so the
-! local array of the type-2 eigenpairs IS the global matrix and main.f90's writers, get_ipratios and the verifier
-! work unchanged.  NOTE: this file cannot be compiled in the development image (no Fortran toolchain); it is
+! Deployment modes:
+!  * one MPI rank (mpirun -np 1): the BLACS grid is 1x1, so the local array of the type-2 eigenpairs IS the global
+!    matrix and main.f90's writers, get_ipratios and the verifier work unchanged;
+!  * one MPI rank per B200 (mpirun -np P, P = 2/4/8 on one box): the grid must be 1 x P (layout_procs,
+!    processes.f90:56-65, gives 1x2, 2x2, 2x4); the case arms of eigen_solver call regrid_1xp(proc) first, which
+!    swaps the grid of setup_distribution for a 1 x P one and returns it in `proc`, so main.f90's later consumers
+!    (get_ipratios' overlap matrix, the verifier) allocate on the same grid as the eigenvectors.  Rank 0 draws the NCCL id
+!    (ekb200_comm_unique_id), mpi_bcast hands it over, every rank calls ekb200_comm_init, and the SAME
+!    ekb200_sygvd_coo call then runs sharded: replicated COO in (as every rank of the reference already holds it,
+!    matrix_io.f90:91-144), all eigenvalues + the rank's column slab of the eigenvectors out.  The slab width is
+!    used as the block size of the eigenvector descriptor, so the local piece is exactly one block column of a
+!    1 x P block-cyclic matrix and every downstream consumer (pdgemm in the verifier, pdelget in get_ipratios and
+!    the eigenvector printer) sees an ordinary ScaLAPACK matrix.
+! NOTE: this file cannot be compiled in the development image (no Fortran toolchain); it is
 ! kept syntax-careful and uses only iso_c_binding scalars/arrays so that a maintainer can build it with
 ! `make WITH_B200=1` (see INTEGRATION.md).
 module ek_solver_b200_m
@@ -18,7 +29,7 @@ module ek_solver_b200_m
   use ek_processes_m, only : check_master, terminate
   implicit none
   private
-  public :: solve_with_b200, solve_with_general_b200
+  public :: solve_with_b200, solve_with_general_b200, regrid_1xp
 
   interface
     integer(c_int) function ekb200_create(ctx, device) bind(C, name='ekb200_create')
@@ -39,6 +50,25 @@ module ek_solver_b200_m
       real(c_double), intent(in) :: vA(*), vB(*)
       real(c_double), intent(out) :: w(*), Z(ldz, *)
     end function ekb200_sygvd_coo
+    integer(c_int) function ekb200_device_count() bind(C, name='ekb200_device_count')
+      import :: c_int
+    end function ekb200_device_count
+    integer(c_int) function ekb200_comm_unique_id(id128) bind(C, name='ekb200_comm_unique_id')
+      import :: c_int, c_char
+      character(kind=c_char), intent(out) :: id128(128)
+    end function ekb200_comm_unique_id
+    integer(c_int) function ekb200_comm_init(ctx, nranks, rank, id128) bind(C, name='ekb200_comm_init')
+      import :: c_ptr, c_int, c_char
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: nranks, rank
+      character(kind=c_char), intent(in) :: id128(128)
+    end function ekb200_comm_init
+    integer(c_int) function ekb200_comm_slab(ctx, ncols, col0, nloc) bind(C, name='ekb200_comm_slab')
+      import :: c_ptr, c_int, c_int64_t
+      type(c_ptr), value :: ctx
+      integer(c_int64_t), value :: ncols
+      integer(c_int64_t), intent(out) :: col0, nloc
+    end function ekb200_comm_slab
     integer(c_int) function ekb200_num_events(ctx) bind(C, name='ekb200_num_events')
       import :: c_ptr, c_int
       type(c_ptr), value :: ctx
@@ -54,6 +84,22 @@ module ek_solver_b200_m
   end interface
 
 contains
+
+  ! The B200 solvers distribute by eigenvector columns: one process column per GPU.  Replaces the grid made by
+  ! setup_distribution (processes.f90:17-36) with a 1 x P grid on the same ranks.
+  subroutine regrid_1xp(proc)
+    type(ek_process_t), intent(inout) :: proc
+    if (proc%n_procs_row == 1) return
+    call blacs_gridexit(proc%context)
+    call blacs_get(-1, 0, proc%context)
+    call blacs_gridinit(proc%context, 'R', 1, proc%n_procs)
+    call blacs_gridinfo(proc%context, proc%n_procs_row, proc%n_procs_col, proc%my_proc_row, proc%my_proc_col)
+    if (proc%my_rank == 0) then
+      print '("BLACS process grid (b200): ", I0, " x ", I0, " (", I0, ")")', &
+           proc%n_procs_row, proc%n_procs_col, proc%n_procs
+    end if
+  end subroutine regrid_1xp
+
 
   ! Replays the library's CUDA-event timing table through add_event (src/event_logger.f90:23-65).
   subroutine replay_events(ctx)
@@ -87,27 +133,43 @@ contains
     type(ek_sparse_mat_t), intent(in), optional :: matrix_B
     type(ek_eigenpairs_types_union_t), intent(out) :: eigenpairs
 
+    include 'mpif.h'
     type(c_ptr) :: ctx
-    integer(c_int) :: info
-    integer(c_int64_t) :: nnzB
+    integer(c_int) :: info, n_dev
+    integer(c_int64_t) :: nnzB, col0, nloc, slab_width
     integer(c_int32_t), allocatable :: ij_dummy(:, :)
     real(c_double), allocatable :: v_dummy(:)
+    character(kind=c_char) :: nccl_id(128)
+    integer :: ierr
 
-    if (proc%n_procs_row /= 1 .or. proc%n_procs_col /= 1) then
-      call terminate('solver_b200: run with one MPI rank (1x1 grid); the GPUs are driven by the library', 1)
+    if (proc%n_procs_row /= 1) then
+      call terminate('solver_b200: the process grid must be 1 x P (one process column per B200)', 1)
     end if
+    n_dev = ekb200_device_count()
+    if (n_dev < 1) call terminate('solver_b200: no usable CUDA device (there is no CPU fallback)', 1)
 
-    eigenpairs%type_number = 2
-    allocate(eigenpairs%blacs%values(n))
-    ! n x n_vec local array + live descriptor on the 1x1 grid (consumers call blacs_gridinfo on desc(context_))
-    call setup_distributed_matrix('Eigenvectors', proc, n, n_vec, &
-         eigenpairs%blacs%desc, eigenpairs%blacs%Vectors)
-
-    info = ekb200_create(ctx, 0_c_int)
+    ! one context per rank on device (rank mod devices); ranks of one box share its GPUs one to one
+    info = ekb200_create(ctx, int(mod(proc%my_rank, n_dev), c_int))
     if (info /= 0) then
       if (check_master()) print '("info(ekb200_create): ", i0)', info
       call terminate('solver_b200: no usable CUDA device (there is no CPU fallback)', info)
     end if
+    if (proc%n_procs > 1) then
+      if (proc%my_rank == 0) info = ekb200_comm_unique_id(nccl_id)
+      call mpi_bcast(nccl_id, 128, mpi_byte, 0, mpi_comm_world, ierr)
+      info = ekb200_comm_init(ctx, int(proc%n_procs, c_int), int(proc%my_rank, c_int), nccl_id)
+      if (info /= 0) call terminate('solver_b200: NCCL communicator could not be created', info)
+    end if
+
+    eigenpairs%type_number = 2
+    allocate(eigenpairs%blacs%values(n))
+    ! n x n_vec eigenvectors on the 1 x P grid, ONE block column per rank: block size = slab width of rank 0 (the
+    ! widest); on one rank this is the plain n x n_vec local array.  Consumers call blacs_gridinfo on desc(context_).
+    info = ekb200_comm_slab(ctx, int(n_vec, c_int64_t), col0, nloc)
+    slab_width = nloc
+    call mpi_bcast(slab_width, 1, mpi_integer8, 0, mpi_comm_world, ierr)
+    call setup_distributed_matrix('Eigenvectors', proc, n, n_vec, &
+         eigenpairs%blacs%desc, eigenpairs%blacs%Vectors, block_size = int(max(slab_width, 1_c_int64_t)))
 
     if (present(matrix_B)) then
       info = ekb200_sygvd_coo(ctx, int(n, c_int64_t), int(n_vec, c_int64_t), &

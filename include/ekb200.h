@@ -32,6 +32,7 @@ const char* ekb200_last_error(const ekb200_ctx* ctx);
 int ekb200_set_option(ekb200_ctx* ctx, const char* key, int64_t value); /* "band" = half bandwidth b (32|64); "profile_gemm" = 0|1;
                                                                            "cache_device_memory" = 1|0 (caching arena; 0 also trims) */
 int ekb200_version(void);
+int ekb200_device_count(void); /* visible CUDA devices (0 when there is none); a rank uses device = local rank */
 
 /* ---- timing table (replaces add_event, src/event_logger.f90:23-65; seconds are CUDA-event times) */
 int ekb200_num_events(const ekb200_ctx* ctx);
