@@ -255,7 +255,9 @@ static int potrf_dist_rec(Ctx* ctx, i64 n, double* A, i64 lda, double* invd, i64
       p.alpha = -1.0; p.beta = 1.0;
       EKB_TRY(gemm(ctx, GEMM_TB, p, /*tri_keep=*/1));
     }
-    EKB_TRY(comm_allgather_cols(ctx, A22, lda, cb));
+    // whole columns of the enclosing matrix (row 0 .. ld): starting at row goff + n1 instead would run the last
+    // slab past the end of the allocation by that many elements
+    EKB_TRY(comm_allgather_cols(ctx, A22 - (goff + n1), lda, cb));
   }
   return potrf_dist_rec(ctx, n2, A22, lda, invd + (n1 / NB) * NB * NB, goff + n1, tmp, pack);
 }

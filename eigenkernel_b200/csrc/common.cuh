@@ -72,7 +72,8 @@ struct Ctx {
     cudaError_t _e = (call);                                                                \
     if (_e != cudaSuccess) {                                                                \
       ctx->last_cuda = _e;                                                                  \
-      ctx->last_error = std::string(#call) + ": " + cudaGetErrorString(_e);                 \
+      ctx->last_error = std::string(#call) + ": " + cudaGetErrorString(_e) + " [" + __FILE__ + ":" +  \
+                        std::to_string(__LINE__) + ", stage " + ctx->cur_stage + "]";       \
       return EKB_ERR_CUDA;                                                                  \
     }                                                                                       \
   } while (0)

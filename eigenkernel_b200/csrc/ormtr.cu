@@ -455,7 +455,7 @@ int apply_q2(Ctx* ctx, i64 n, int b, const double* V2, i64 ldv, const double* TA
 }
 
 // ------------------------------------------------------------------------------------------ q1
-constexpr int Q1_GROUP = 4;  // panels aggregated into one WY block
+constexpr int Q1_GROUP = 8;  // panels aggregated into one WY block
 
 // Explicit zeros above every panel inside its group: rows [j0+b, j+b) of panel columns [j, j+b).
 __global__ void q1_zero_above_kernel(double* __restrict__ A, i64 lda, int b, int npan, int group) {
