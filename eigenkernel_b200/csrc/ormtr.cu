@@ -167,8 +167,9 @@ __device__ __forceinline__ void q2_mbar_wait(unsigned long long* bar, unsigned p
 }
 __device__ __forceinline__ void q2_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
-// One CTA owns 16 NW columns of Z and walks every diamond block (S descending, t ascending).  Each WARP owns 16
-// of those columns and keeps its HP x 16 piece of the moving window in REGISTERS, as DMMA accumulator tiles
+// One CTA owns 8 NJ NW columns of Z and walks every diamond block (S descending, t ascending).  Each WARP owns 8 NJ
+// of those columns (NJ = 2 normally, 1 for narrow slabs) and keeps its HP x 8 NJ piece of the moving window in
+// REGISTERS, as DMMA accumulator tiles
 // (thread (lq,lr) holds rows 8 rho + 2 lr + {0,1} of column lq), for the whole walk:
 //     W = Y^T Zw     the Z tiles are used directly as the k-side MMA operand: within an 8-row tile the two
 //                    DMMA.8x8x4 steps take k = {2 lr} and k = {2 lr + 1} (a permutation of the summation
@@ -179,7 +180,7 @@ __device__ __forceinline__ void q2_fence_proxy_async() { asm volatile("fence.pro
 // ONE cp.async.bulk (TMA, mbarrier completion) one block ahead), read with conflict-free 128-bit loads, 0.25 loads per DMMA.  Rows that leave the
 // window are stored from registers, rows that enter are prefetched into registers one step ahead.  Every
 // global element is always touched by the same thread, so program order is all the ordering the walk needs.
-template <int B, int NBS, int NW, bool AL16>
+template <int B, int NBS, int NW, bool AL16, int NJ>
 __global__ void __launch_bounds__(32 * NW, 1) q2_apply_kernel(const double* __restrict__ packed,
                                                              const i64* __restrict__ blk_off, i64 n, int nS,
                                                              double* __restrict__ Z, i64 ldz, i64 k) {
@@ -190,12 +191,12 @@ __global__ void __launch_bounds__(32 * NW, 1) q2_apply_kernel(const double* __re
   extern __shared__ __align__(16) double sm[];  // two image buffers
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int lq = lane >> 2, lr = lane & 3;
-  const i64 cwarp = (i64)blockIdx.x * (16 * NW) + 16 * warp;  // first column of this warp
-  const bool cols_full = cwarp + 16 <= k;                     // warp-uniform
-  double* zc[2];
-  bool cv[2];
+  const i64 cwarp = (i64)blockIdx.x * (8 * NJ * NW) + 8 * NJ * warp;  // first column of this warp
+  const bool cols_full = cwarp + 8 * NJ <= k;                     // warp-uniform
+  double* zc[NJ];
+  bool cv[NJ];
 #pragma unroll
-  for (int j = 0; j < 2; ++j) {
+  for (int j = 0; j < NJ; ++j) {
     cv[j] = cwarp + lq + 8 * j < k;
     zc[j] = Z + (cv[j] ? (cwarp + lq + 8 * j) * ldz : 0) + 2 * lr;  // row offset 2 lr folded in
   }
@@ -246,8 +247,8 @@ __global__ void __launch_bounds__(32 * NW, 1) q2_apply_kernel(const double* __re
   };
   unsigned phase = 0;  // bit b: parity to wait for on bars[b]
 
-  double zacc[TILES][2][2];   // the window
-  double zin[SHIFT][2][2];    // rows entering at the next step
+  double zacc[TILES][NJ][2];   // the window
+  double zin[SHIFT][NJ][2];    // rows entering at the next step
 
   int S = nS - 1;
   while (S >= 0 && q2_num_tasks(n, B, (i64)S * NBS) == 0) --S;
@@ -266,7 +267,7 @@ __global__ void __launch_bounds__(32 * NW, 1) q2_apply_kernel(const double* __re
 #pragma unroll
       for (int r = 0; r < TILES; ++r)
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
+        for (int j = 0; j < NJ; ++j) {
           const double2 v = ld2(s0 + 8 * r, j, fast);
           zacc[r][j][0] = v.x + 0.0;
           zacc[r][j][1] = v.y + 0.0;
@@ -287,18 +288,18 @@ __global__ void __launch_bounds__(32 * NW, 1) q2_apply_kernel(const double* __re
 #pragma unroll
         for (int q = 0; q < SHIFT; ++q)
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
+          for (int j = 0; j < NJ; ++j) {
             const double2 v = ld2(W0 + G::HP + 8 * q, j, fast);
             zin[q][j][0] = v.x;
             zin[q][j][1] = v.y;
           }
       }
       // ---- product 1: W(i,c) = sum_r' Y(r',i) Zw(r',c)
-      double wacc[MI][2][2];
+      double wacc[MI][NJ][2];
 #pragma unroll
       for (int a = 0; a < MI; ++a)
 #pragma unroll
-        for (int j = 0; j < 2; ++j) wacc[a][j][0] = wacc[a][j][1] = 0.0;
+        for (int j = 0; j < NJ; ++j) wacc[a][j][0] = wacc[a][j][1] = 0.0;
       {
         const double* yp = Ys + lq * LDY + 2 * lr;
 #pragma unroll
@@ -308,7 +309,7 @@ __global__ void __launch_bounds__(32 * NW, 1) q2_apply_kernel(const double* __re
             if (r >= a) {  // Y(r',i) == 0 for r' <= i
               const double2 y = *reinterpret_cast<const double2*>(yp + a * 8 * LDY + 8 * r);
 #pragma unroll
-              for (int j = 0; j < 2; ++j) {
+              for (int j = 0; j < NJ; ++j) {
                 dmma884_(wacc[a][j][0], wacc[a][j][1], zacc[r][j][0], y.x);
                 dmma884_(wacc[a][j][0], wacc[a][j][1], zacc[r][j][1], y.y);
               }
@@ -324,7 +325,7 @@ __global__ void __launch_bounds__(32 * NW, 1) q2_apply_kernel(const double* __re
             if (r >= a && r <= a + B / 8) {  // V(r',i) != 0 only for i < r' <= i + B
               const double2 v = *reinterpret_cast<const double2*>(vp + r * 8 * LDVT + 8 * a);
 #pragma unroll
-              for (int j = 0; j < 2; ++j) {
+              for (int j = 0; j < NJ; ++j) {
                 dmma884_(zacc[r][j][0], zacc[r][j][1], wacc[a][j][0], v.x);
                 dmma884_(zacc[r][j][0], zacc[r][j][1], wacc[a][j][1], v.y);
               }
@@ -337,18 +338,18 @@ __global__ void __launch_bounds__(32 * NW, 1) q2_apply_kernel(const double* __re
 #pragma unroll
           for (int r = 0; r < SHIFT; ++r)
 #pragma unroll
-            for (int j = 0; j < 2; ++j) st2(W0 + 8 * r, j, fast, zacc[r][j][0], zacc[r][j][1]);
+            for (int j = 0; j < NJ; ++j) st2(W0 + 8 * r, j, fast, zacc[r][j][0], zacc[r][j][1]);
 #pragma unroll
           for (int r = 0; r < KEEP; ++r)
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
+            for (int j = 0; j < NJ; ++j) {
               zacc[r][j][0] = zacc[r + SHIFT][j][0];
               zacc[r][j][1] = zacc[r + SHIFT][j][1];
             }
 #pragma unroll
           for (int q = 0; q < SHIFT; ++q)
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
+            for (int j = 0; j < NJ; ++j) {
               zacc[KEEP + q][j][0] = zin[q][j][0];
               zacc[KEEP + q][j][1] = zin[q][j][1];
             }
@@ -356,7 +357,7 @@ __global__ void __launch_bounds__(32 * NW, 1) q2_apply_kernel(const double* __re
 #pragma unroll
           for (int r = 0; r < TILES; ++r)
 #pragma unroll
-            for (int j = 0; j < 2; ++j) st2(W0 + 8 * r, j, fast, zacc[r][j][0], zacc[r][j][1]);
+            for (int j = 0; j < NJ; ++j) st2(W0 + 8 * r, j, fast, zacc[r][j][0], zacc[r][j][1]);
         }
       }
       buf ^= 1;
@@ -366,27 +367,31 @@ __global__ void __launch_bounds__(32 * NW, 1) q2_apply_kernel(const double* __re
 
 // Work per SM is what bounds the walk (every CTA is a serial chain over all diamond blocks): choose the slab
 // width that minimises ceil(#CTA / #SM) * KC, the columns the busiest SM has to process.
-template <int NW>
+// NJ = accumulator column tiles per warp: 2 (16 columns) normally; 1 (8 columns per warp) doubles the number of
+// warps when a rank's slab is too narrow to give every scheduler of every SM a warp (multi-GPU column slabs).
+// The choice is returned as NW + 100 * (NJ == 1).
+template <int NW, int NJ>
 static void q2_consider(Ctx* ctx, i64 k, int force_kc, long long* best_cost, int* best_nw) {
-  constexpr int KC = 16 * NW;
-  if (force_kc > 0 && force_kc != KC) return;
+  constexpr int KC = 8 * NJ * NW;
+  if (force_kc > 0 && (force_kc != KC || NJ != 2)) return;
   const long long nct = (k + KC - 1) / KC;
   const long long cost = ((nct + ctx->num_sms - 1) / ctx->num_sms) * KC;
-  if (*best_nw == 0 || cost < *best_cost || (cost == *best_cost && NW > *best_nw)) {
+  const int code = NW + (NJ == 1 ? 100 : 0);
+  if (*best_nw == 0 || cost < *best_cost || (cost == *best_cost && NJ == 2 && (*best_nw > 100 || NW > *best_nw))) {
     *best_cost = cost;
-    *best_nw = NW;
+    *best_nw = code;
   }
 }
 
-template <int B, int NBS, int NW, bool AL16>
+template <int B, int NBS, int NW, bool AL16, int NJ = 2>
 static cudaError_t q2_apply_launch(Ctx* ctx, const double* packed, const i64* d_off, i64 n, int nS, double* Z, i64 ldz,
                                    i64 k) {
   using G = Q2Geom<B, NBS>;
   const size_t smem = (size_t)2 * G::IMG * sizeof(double);
-  auto kern = q2_apply_kernel<B, NBS, NW, AL16>;
+  auto kern = q2_apply_kernel<B, NBS, NW, AL16, NJ>;
   cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (ce != cudaSuccess) return ce;
-  kern<<<cdiv(k, 16 * NW), 32 * NW, smem, ctx->stream>>>(packed, d_off, n, nS, Z, ldz, k);
+  kern<<<cdiv(k, 8 * NJ * NW), 32 * NW, smem, ctx->stream>>>(packed, d_off, n, nS, Z, ldz, k);
   EKB_COUNT_LAUNCH(ctx);
   return cudaGetLastError();
 }
@@ -417,11 +422,13 @@ static int q2_launch(Ctx* ctx, i64 n, const double* V2, i64 ldv, const double* T
   if (ce == cudaSuccess) {
     long long cost = 0;
     int nw = 0;
-    q2_consider<4>(ctx, k, ctx->q2_kc, &cost, &nw);
-    q2_consider<5>(ctx, k, ctx->q2_kc, &cost, &nw);
-    q2_consider<6>(ctx, k, ctx->q2_kc, &cost, &nw);
-    q2_consider<7>(ctx, k, ctx->q2_kc, &cost, &nw);
-    q2_consider<8>(ctx, k, ctx->q2_kc, &cost, &nw);
+    q2_consider<4, 2>(ctx, k, ctx->q2_kc, &cost, &nw);
+    q2_consider<5, 2>(ctx, k, ctx->q2_kc, &cost, &nw);
+    q2_consider<6, 2>(ctx, k, ctx->q2_kc, &cost, &nw);
+    q2_consider<7, 2>(ctx, k, ctx->q2_kc, &cost, &nw);
+    q2_consider<8, 2>(ctx, k, ctx->q2_kc, &cost, &nw);
+    q2_consider<4, 1>(ctx, k, ctx->q2_kc, &cost, &nw);
+    q2_consider<8, 1>(ctx, k, ctx->q2_kc, &cost, &nw);
     const bool al16 = ((uintptr_t)Z & 15) == 0 && (ldz & 1) == 0;
     if (!al16) nw = -4;  // 8-byte global accesses: one generic instantiation
     prof_begin(ctx, PROF_Q2_APPLY, 2.0 * (double)n * (double)n * (double)k);
@@ -432,6 +439,8 @@ static int q2_launch(Ctx* ctx, i64 n, const double* V2, i64 ldv, const double* T
       case 6: ce = q2_apply_launch<B, NBS, 6, true>(ctx, packed, d_off, n, nS, Z, ldz, k); break;
       case 7: ce = q2_apply_launch<B, NBS, 7, true>(ctx, packed, d_off, n, nS, Z, ldz, k); break;
       case 8: ce = q2_apply_launch<B, NBS, 8, true>(ctx, packed, d_off, n, nS, Z, ldz, k); break;
+      case 104: ce = q2_apply_launch<B, NBS, 4, true, 1>(ctx, packed, d_off, n, nS, Z, ldz, k); break;
+      case 108: ce = q2_apply_launch<B, NBS, 8, true, 1>(ctx, packed, d_off, n, nS, Z, ldz, k); break;
       default: ce = cudaErrorInvalidValue;
     }
     prof_end(ctx);

@@ -8,10 +8,14 @@ from test_gpu_twostage import _run_sb2st, q1_from_panels, q2_from_reflectors
 pytestmark = pytest.mark.gpu
 
 
+# kc = 0: the library picks the slab width (narrow right-hand sides take the 8-columns-per-warp kernel);
+# kc = 64 / 112 force the 16-columns-per-warp kernels the full-width solve uses
+@pytest.mark.parametrize("kc", [0, 64, 112])
 @pytest.mark.parametrize("n,band,k", [(3, 64, 3), (40, 64, 40), (66, 64, 17), (130, 64, 130), (200, 32, 64),
                                       (333, 64, 333), (500, 64, 65), (700, 32, 700)])
-def test_apply_q2_matches_explicit_product(ctx, n, band, k):
+def test_apply_q2_matches_explicit_product(ctx, n, band, k, kc):
     ctx.set_option("band", band)
+    ctx.set_option("q2_kc", kc)
     try:
         b = band
         rng = np.random.default_rng(n + k)
@@ -30,6 +34,7 @@ def test_apply_q2_matches_explicit_product(ctx, n, band, k):
             x.free()
     finally:
         ctx.set_option("band", 64)
+        ctx.set_option("q2_kc", 0)
 
 
 @pytest.mark.parametrize("n,band,k", [(67, 64, 67), (130, 64, 5), (300, 64, 300), (300, 32, 77), (390, 64, 390),
