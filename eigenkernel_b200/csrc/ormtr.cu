@@ -365,19 +365,24 @@ __global__ void __launch_bounds__(32 * NW, 1) q2_apply_kernel(const double* __re
   }
 }
 
-// Work per SM is what bounds the walk (every CTA is a serial chain over all diamond blocks): choose the slab
-// width that minimises ceil(#CTA / #SM) * KC, the columns the busiest SM has to process.
+// Every CTA is a serial chain over all diamond blocks, so the walk takes (waves of CTAs) x (time of one CTA).
+// Measured on B200 (scripts/q2_slab_probe.py, n = 16384: 166 / 245 / 337 ms for 4 / 8 / 12 warps of 8 columns,
+// 323 / 448 ms for 4 / 7 warps of 16 columns) the time of one CTA is proportional to NJ (4.4 + NW): a lone warp per
+// scheduler is latency-bound, more and thinner warps interleave on the DMMA pipe.
 // NJ = accumulator column tiles per warp: 2 (16 columns) normally; 1 (8 columns per warp) doubles the number of
 // warps when a rank's slab is too narrow to give every scheduler of every SM a warp (multi-GPU column slabs).
 // The choice is returned as NW + 100 * (NJ == 1).
 template <int NW, int NJ>
 static void q2_consider(Ctx* ctx, i64 k, int force_kc, long long* best_cost, int* best_nw) {
   constexpr int KC = 8 * NJ * NW;
-  if (force_kc > 0 && (force_kc != KC || NJ != 2)) return;
+  // q2_kc forces a kernel: 64..128 = 16-columns-per-warp with that many columns per CTA; 1000 + NW = the
+  // 8-columns-per-warp kernel with NW warps
+  if (force_kc >= 1000 && (NJ != 1 || force_kc != 1000 + NW)) return;
+  if (force_kc > 0 && force_kc < 1000 && (force_kc != KC || NJ != 2)) return;
   const long long nct = (k + KC - 1) / KC;
-  const long long cost = ((nct + ctx->num_sms - 1) / ctx->num_sms) * KC;
+  const long long cost = ((nct + ctx->num_sms - 1) / ctx->num_sms) * NJ * (44 + 10 * NW);
   const int code = NW + (NJ == 1 ? 100 : 0);
-  if (*best_nw == 0 || cost < *best_cost || (cost == *best_cost && NJ == 2 && (*best_nw > 100 || NW > *best_nw))) {
+  if (*best_nw == 0 || cost < *best_cost) {
     *best_cost = cost;
     *best_nw = code;
   }
@@ -429,6 +434,7 @@ static int q2_launch(Ctx* ctx, i64 n, const double* V2, i64 ldv, const double* T
     q2_consider<8, 2>(ctx, k, ctx->q2_kc, &cost, &nw);
     q2_consider<4, 1>(ctx, k, ctx->q2_kc, &cost, &nw);
     q2_consider<8, 1>(ctx, k, ctx->q2_kc, &cost, &nw);
+    q2_consider<12, 1>(ctx, k, ctx->q2_kc, &cost, &nw);
     const bool al16 = ((uintptr_t)Z & 15) == 0 && (ldz & 1) == 0;
     if (!al16) nw = -4;  // 8-byte global accesses: one generic instantiation
     prof_begin(ctx, PROF_Q2_APPLY, 2.0 * (double)n * (double)n * (double)k);
@@ -441,6 +447,7 @@ static int q2_launch(Ctx* ctx, i64 n, const double* V2, i64 ldv, const double* T
       case 8: ce = q2_apply_launch<B, NBS, 8, true>(ctx, packed, d_off, n, nS, Z, ldz, k); break;
       case 104: ce = q2_apply_launch<B, NBS, 4, true, 1>(ctx, packed, d_off, n, nS, Z, ldz, k); break;
       case 108: ce = q2_apply_launch<B, NBS, 8, true, 1>(ctx, packed, d_off, n, nS, Z, ldz, k); break;
+      case 112: ce = q2_apply_launch<B, NBS, 12, true, 1>(ctx, packed, d_off, n, nS, Z, ldz, k); break;
       default: ce = cudaErrorInvalidValue;
     }
     prof_end(ctx);

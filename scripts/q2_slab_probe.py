@@ -23,7 +23,7 @@ ctx.call("ekb200_sb2st", n, dAB, 2 * b, dV2, ld, dTAU, ntm, dd, de)
 sec = ctypes.c_double()
 for k in ks:
     dZ = ctx.alloc(ld * k * 8)
-    for kc in (0, 64):
+    for kc in [int(x) for x in (sys.argv[3].split(",") if len(sys.argv) > 3 else "0,64".split(","))]:
         ctx.set_option("q2_kc", kc)
         best = 1e9
         for rep in range(3):

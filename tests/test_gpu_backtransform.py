@@ -9,8 +9,9 @@ pytestmark = pytest.mark.gpu
 
 
 # kc = 0: the library picks the slab width (narrow right-hand sides take the 8-columns-per-warp kernel);
-# kc = 64 / 112 force the 16-columns-per-warp kernels the full-width solve uses
-@pytest.mark.parametrize("kc", [0, 64, 112])
+# kc = 64 / 112 force the 16-columns-per-warp kernels the full-width solve uses, 1008 / 1012 the 8-per-warp ones
+# with 8 / 12 warps
+@pytest.mark.parametrize("kc", [0, 64, 112, 1008, 1012])
 @pytest.mark.parametrize("n,band,k", [(3, 64, 3), (40, 64, 40), (66, 64, 17), (130, 64, 130), (200, 32, 64),
                                       (333, 64, 333), (500, 64, 65), (700, 32, 700)])
 def test_apply_q2_matches_explicit_product(ctx, n, band, k, kc):
