@@ -46,11 +46,25 @@ __global__ void __launch_bounds__(QR_THREADS) panel_qr_kernel(double* __restrict
     double scal = 0.0, tj = 0.0;
     if (j >= 0) {
       // reduce the partial dot products of column j with columns j..B-1 (rows > j)
+      // all threads take part (QR_THREADS / B interleaved slices of the G partials per column, loads batched):
+      // a single thread per column walking G dependent L2 loads used to dominate the time of a column step
       const double* pp = partial + (size_t)(j & 1) * G * B;
-      if (tid < B) {
+      {
+        constexpr int NPART = QR_THREADS / B;
+        const int c = tid % B, part = tid / B;
         double s = 0.0;
-        if (tid >= j)
-          for (int q = 0; q < G; ++q) s += pp[q * B + tid];
+        if (c >= j) {
+#pragma unroll 8
+          for (int q = part; q < G; q += NPART) s += __ldcg(pp + q * B + c);
+        }
+        red[part][c] = s;
+      }
+      __syncthreads();
+      if (tid < B) {
+        constexpr int NPART = QR_THREADS / B;
+        double s = 0.0;
+#pragma unroll
+        for (int q = 0; q < NPART; ++q) s += red[q][tid];
         g[tid] = s;
       }
       __syncthreads();
