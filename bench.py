@@ -39,6 +39,28 @@ UNIT = "TFLOP/s"
 SEED = 20240602
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout() -> None:
+    """Rank 0's stdout must carry exactly ONE JSON line: route everything libraries print to fd 1 (NCCL's version
+    banner, for one) to stderr and keep the real stdout for emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def canonical_flops(n: int) -> float:
     return 7.0 * float(n) ** 3  # BASELINE.md 5: n^3/3 + n^3 + 4n^3/3 + 4n^3/3 + 2n^3 + n^3
 
@@ -94,7 +116,7 @@ def run_reference(args) -> None:
                          "stage_seconds": stages},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------ clocks
@@ -366,7 +388,7 @@ def run_ours(args) -> None:
         "gpu_launches": int(launches), "nccl_collectives": int(collectives), "roofline": roof, "stages": stages,
         "kernel_profile": prof_rows, "fp64_peak_measured": peak, "cpu_baseline": cpu,
     }
-    print(json.dumps(line))
+    emit(line)
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()
@@ -383,6 +405,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
