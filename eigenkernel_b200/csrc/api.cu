@@ -108,6 +108,11 @@ int ekb200_set_option(ekb200_ctx* h, const char* key, int64_t value) {
     ctx->band = (int)value;
     return 0;
   }
+  if (!strcmp(key, "reduction")) {  // 0: blocked pdsygst-style reduction (default); 1: explicit inverse of L
+    if (value != 0 && value != 1) return -3;
+    ctx->reduction = (int)value;
+    return 0;
+  }
   if (!strcmp(key, "q2_kc")) {
     if (value != 0 && value != 1004 && value != 1008 && value != 1012 && (value < 64 || value > 128 || value % 16))
       return -3;

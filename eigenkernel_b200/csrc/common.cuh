@@ -45,6 +45,7 @@ struct Ctx {
   int* h_info = nullptr;              // pinned mirror
   // options
   int band = 64;                      // b: half bandwidth of the two-stage reduction
+  int reduction = 0;                  // 0: blocked pdsygst-style reduction; 1: explicit inverse (ELPA-style)
   int q2_kc = 0;                      // columns of Z per CTA in apply_q2 (0 = choose; 64|80|96|112|128)
   // stage timers
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -148,6 +149,10 @@ enum TrsmKind { TRSM_RLT = 0 /* X L^T = B */, TRSM_LLN = 1 /* L X = B */, TRSM_L
 int trsm_lower(Ctx* ctx, int kind, i64 m, i64 n, const double* L, i64 ldl, const double* invd, double* Bm, i64 ldb);
 int trtri_diag_blocks(Ctx* ctx, i64 n, const double* L, i64 ldl, double* invd);
 int sygst_lower(Ctx* ctx, i64 n, double* A, i64 lda, const double* L, i64 ldl, const double* invd);
+// explicit-inverse reduction (option "reduction" = 1): X = L^-1, A <- X A X^T, Z <- X^T Z
+int trtri_lower(Ctx* ctx, i64 n, const double* L, i64 ldl, const double* invd, double* X, i64 ldx);
+int sygst_inverse(Ctx* ctx, i64 n, double* A, i64 lda, const double* X, i64 ldx, double* C, i64 ldc);
+int trmm_lower_t(Ctx* ctx, i64 n, i64 k, const double* X, i64 ldx, double* Z, i64 ldz);
 
 // two-stage tridiagonalization
 size_t sy2sb_workspace_doubles(i64 n, int b, int num_sms);

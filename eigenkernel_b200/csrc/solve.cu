@@ -129,6 +129,9 @@ int sygvd_dev(Ctx* ctx, i64 n, i64 nev, double* A, i64 lda, double* B, i64 ldb, 
               double* invd, double* merge_flops) {
   if (n <= 0 || nev <= 0) return 0;
   StageTimer total(ctx, "solve_with_general_b200");
+  Scratch sc(ctx);
+  double* X = nullptr;  // L^-1 of the explicit-inverse variant (option "reduction" = 1), kept for the recovery
+  const i64 ldx = round_up(n, 8);
   {
     StageTimer red(ctx, "reduce_generalized_b200");
     {
@@ -137,7 +140,26 @@ int sygvd_dev(Ctx* ctx, i64 n, i64 nev, double* A, i64 lda, double* B, i64 ldb, 
       t.stop();
       if (rc) return rc;  // > 0: order of the leading minor that is not positive definite (info(pdpotrf))
     }
-    {
+    if (ctx->reduction == 1) {
+      // ELPA-style workflow (reference src/solver_elpa_eigenexa.f90:110-150): invert the factor, two multiplies.
+      // Replicated on every rank (deterministic kernels: identical bits); the recovery acts on the rank's slab.
+      EKB_TRY(sc.get((void**)&X, (size_t)ldx * n * sizeof(double)));
+      {
+        StageTimer t(ctx, "reduce_generalized_b200:trtri");
+        int rc = trtri_lower(ctx, n, B, ldb, invd, X, ldx);
+        t.stop();
+        if (rc) return rc;
+      }
+      {
+        StageTimer t(ctx, "reduce_generalized_b200:multiply");
+        double* C = nullptr;
+        EKB_TRY(sc.get((void**)&C, (size_t)ldx * n * sizeof(double)));
+        int rc = sygst_inverse(ctx, n, A, lda, X, ldx, C, ldx);
+        t.stop();
+        sc.release(C);
+        if (rc) return rc;
+      }
+    } else {
       StageTimer t(ctx, "reduce_generalized_b200:sygst");
       int rc = sygst_dist(ctx, n, A, lda, B, ldb, invd);
       t.stop();
@@ -151,7 +173,10 @@ int sygvd_dev(Ctx* ctx, i64 n, i64 nev, double* A, i64 lda, double* B, i64 ldb, 
     std::vector<i64> zb;
     slab_bounds(nev, ctx->nranks, 128, zb);
     const i64 c0 = zb[ctx->rank], kc = zb[ctx->rank + 1] - zb[ctx->rank];
-    int rc = kc > 0 ? trsm_lower(ctx, TRSM_LLT, n, kc, B, ldb, invd, Z + c0 * ldz, ldz) : 0;
+    int rc = 0;
+    if (kc > 0)
+      rc = X ? trmm_lower_t(ctx, n, kc, X, ldx, Z + c0 * ldz, ldz)  // Z <- L^-T Z as a product (pdtrmm_EV)
+             : trsm_lower(ctx, TRSM_LLT, n, kc, B, ldb, invd, Z + c0 * ldz, ldz);
     t.stop();
     if (rc) return rc;
   }

@@ -30,7 +30,9 @@ int ekb200_destroy(ekb200_ctx* ctx);
 const char* ekb200_strerror(int info);
 const char* ekb200_last_error(const ekb200_ctx* ctx);
 int ekb200_set_option(ekb200_ctx* ctx, const char* key, int64_t value); /* "band" = half bandwidth b (32|64); "profile_gemm" = 0|1;
-                                                                           "cache_device_memory" = 1|0 (caching arena; 0 also trims) */
+                                                                           "cache_device_memory" = 1|0 (caching arena; 0 also trims);
+                                                                           "reduction" = 0 blocked pdsygst-style | 1 explicit inverse of
+                                                                           L (-s general_b200inv; solver_elpa_eigenexa.f90:110-150) */
 int ekb200_version(void);
 int ekb200_device_count(void); /* visible CUDA devices (0 when there is none); a rank uses device = local rank */
 

@@ -1,0 +1,247 @@
+"""CPU tests of the C++ host twin of EigenKernel_App (app/): formats, MatrixMarket reader, argument handling and the
+command-line flow up to the solver call.  The formats are checked against the shipped answer files and against the
+Python restatement (eigenkernel_b200/app_io.py), the reader against the fixtures of the reference."""
+import ctypes
+import os
+import random
+import subprocess
+
+import numpy as np
+import pytest
+
+from eigenkernel_b200 import app_io
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+APP = os.path.join(ROOT, "app", "bin", "ekb200_app")
+HOOKS = os.path.join(ROOT, "app", "libekb200_apphooks.so")
+
+
+@pytest.fixture(scope="module")
+def hooks():
+    if not (os.path.exists(APP) and os.path.exists(HOOKS)):
+        import __graft_entry__ as g
+        g.build()
+    lib = ctypes.CDLL(HOOKS)
+    lib.ekapp_fortran_e.argtypes = [ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_char_p, ctypes.c_int]
+    lib.ekapp_log_json.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_double),
+                                   ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_longlong,
+                                   ctypes.c_int, ctypes.c_char_p, ctypes.c_int]
+    lib.ekapp_read_matrix.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(ctypes.c_longlong),
+                                      ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_longlong), ctypes.c_void_p,
+                                      ctypes.c_void_p, ctypes.c_longlong, ctypes.c_char_p, ctypes.c_int]
+    lib.ekapp_parse_ranges.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_longlong), ctypes.c_int, ctypes.c_char_p,
+                                       ctypes.c_int]
+    return lib
+
+
+def _fe(lib, x, w=26, d=16, e=3):
+    buf = ctypes.create_string_buffer(128)
+    lib.ekapp_fortran_e(x, w, d, e, buf, 128)
+    return buf.value.decode()
+
+
+def _read(lib, path, threads=1, with_body=True):
+    rows, cols, ent = ctypes.c_longlong(), ctypes.c_longlong(), ctypes.c_longlong()
+    msg = ctypes.create_string_buffer(256)
+    rc = lib.ekapp_read_matrix(path.encode(), threads, rows, cols, ent, None, None, 0, msg, 256)
+    if rc or not with_body:
+        return rc, (rows.value, cols.value, ent.value), None, None, msg.value.decode()
+    ij = np.zeros((ent.value, 2), dtype=np.int32)
+    v = np.zeros(ent.value)
+    rc = lib.ekapp_read_matrix(path.encode(), threads, rows, cols, ent, ij.ctypes.data, v.ctypes.data, ent.value, msg, 256)
+    return rc, (rows.value, cols.value, ent.value), ij, v, msg.value.decode()
+
+
+def test_edit_descriptors_match_known_values_and_python_restatement(hooks):
+    assert _fe(hooks, -1.121921212197622) == "  -0.1121921212197622E+001"
+    assert _fe(hooks, 0.0) == "   0.0000000000000000E+000"
+    assert _fe(hooks, 9.9999999999999999e-5) == "   0.1000000000000000E-003"
+    assert _fe(hooks, 4.36, 24, 16, 3) == " 0.4360000000000000E+001"
+    assert _fe(hooks, 0.53481162e1, 15, 8, 0) == " 0.53481162E+01"   # the e15.8 of main.f90:153-155
+    assert _fe(hooks, 1.5e-120, 15, 8, 0) == " 0.15000000-119"       # three-digit exponent drops the E
+    rng = random.Random(7)
+    for _ in range(2000):
+        x = rng.uniform(-1, 1) * 10.0 ** rng.randint(-300, 300)
+        assert _fe(hooks, x) == app_io.fortran_e(x)
+        assert _fe(hooks, x, 24, 16, 3) == app_io.fortran_e(x, 24, 16, 3)
+
+
+@pytest.mark.parametrize("name", ["ELSES_MATRIX_BNZ30_ev.txt", "ELSES_MATRIX_BNZ30_ipr.txt"])
+def test_answer_files_reformat_byte_for_byte(hooks, golden_dir, name):
+    """eigenvalues.dat / ipratios.dat lines are '(I8, " ", E26.16e3)' (main.f90:115-117,139-141)."""
+    lines = open(os.path.join(golden_dir, name)).read().splitlines()
+    for ln in lines:
+        j, val = ln.split()
+        assert f"{int(j):8d} {_fe(hooks, float(val))}" == ln
+
+
+def test_log_json_matches_python_restatement(hooks):
+    names = [b"main:read_command_argument", b"read_matrix_file", b"read_matrix_file", b"main"]
+    vals = [1.5e-3, 0.25, 0.5, 12.0]
+    arr_n = (ctypes.c_char_p * 4)(*names)
+    arr_v = (ctypes.c_double * 4)(*vals)
+    buf = ctypes.create_string_buffer(1 << 16)
+    hooks.ekapp_log_json(4, arr_n, arr_v, b"bin/eigenkernel_app -s general_b200 A.mtx B.mtx", b"A.mtx", b"B.mtx",
+                         b"general_b200", 30, 0, buf, 1 << 16)
+    lg = app_io.EventLogger(echo=False)
+    for n, v in zip(names, vals):
+        lg.add_event(n.decode(), v)
+    setting = {"version": "20160808", "command": "bin/eigenkernel_app -s general_b200 A.mtx B.mtx",
+               "matrix_A_filename": "A.mtx", "matrix_B_filename": "B.mtx", "log_filename": "log.json", "dimension": 30,
+               "solver": "general_b200", "g_block_size": 64, "block_size": 0}
+    assert buf.value.decode() == app_io.log_json_text(setting, lg.events)
+
+
+def test_matrix_market_reader_matches_python_reader_on_the_fixtures(hooks, golden_dir):
+    for name, dims in (("ELSES_MATRIX_BNZ30_A.mtx", (30, 30, 303)), ("ELSES_MATRIX_BNZ30_B.mtx", (30, 30, 303)),
+                       ("ELSES_MATRIX_VCNT400std_A.mtx", None)):
+        path = os.path.join(golden_dir, name)
+        rc, got, ij, v, _ = _read(hooks, path)
+        assert rc == 0
+        ref = app_io.read_matrix_file(path)
+        if dims:
+            assert got == dims
+        assert got == (ref.size, ref.size, ref.num_non_zeros)
+        assert np.array_equal(ij, ref.suffix) and np.array_equal(v, ref.value)
+
+
+def test_parallel_parser_is_identical_to_serial(hooks, tmp_path):
+    """the body is split at record boundaries and parsed by several threads."""
+    rng = np.random.default_rng(3)
+    n = 420
+    ii, jj = np.tril_indices(n)
+    vals = rng.standard_normal(ii.size)
+    p = tmp_path / "big.mtx"
+    with open(p, "w") as f:
+        f.write("%%MatrixMarket matrix coordinate real symmetric\n% generated\n%\n")
+        f.write(f"{n} {n} {ii.size}\n")
+        for q, (i, j, x) in enumerate(zip(ii, jj, vals)):
+            if q % 1000 == 7:
+                f.write("\n")                                            # empty records are skipped by list-directed input
+            if q % 3 == 0:
+                f.write(f"  {i + 1}   {j + 1}  {x:.17e}\n")
+            elif q % 3 == 1:
+                f.write(f"{i + 1},{j + 1},{x:.17e}".replace("e", "D") + "\n")  # commas and D exponents
+            else:
+                f.write(f"{i + 1}\t{j + 1}\t{float(x)!r} trailing ignored\n")
+    assert os.path.getsize(p) > (1 << 20)
+    rc1, d1, ij1, v1, _ = _read(hooks, str(p), threads=1)
+    rc4, d4, ij4, v4, _ = _read(hooks, str(p), threads=5)
+    assert rc1 == 0 and rc4 == 0 and d1 == d4 == (n, n, ii.size)
+    assert np.array_equal(ij1, ij4) and np.array_equal(v1, v4)
+    assert np.array_equal(ij1[:, 0], ii + 1) and np.array_equal(ij1[:, 1], jj + 1) and np.array_equal(v1, vals)
+
+
+def test_reader_error_behaviour(hooks, tmp_path):
+    bad = tmp_path / "range.mtx"
+    bad.write_text("%%MatrixMarket matrix coordinate real symmetric\n% c\n3 3 2\n1 1 1.0\n4 1 2.0\n")
+    rc, _, _, _, msg = _read(hooks, str(bad))
+    assert rc >= 1000 and "index of matrix out of range" in msg
+    short = tmp_path / "short.mtx"
+    short.write_text("%%MatrixMarket matrix coordinate real symmetric\n3 3 3\n1 1 1.0\n2 1 2.0\n")
+    rc, _, _, _, msg = _read(hooks, str(short))
+    assert rc >= 1000 and "invalid format of matrix value" in msg
+    junk = tmp_path / "junk.mtx"
+    junk.write_text("%%MatrixMarket matrix coordinate real symmetric\n3 3 1\n1 x 1.0\n")
+    rc, _, _, _, msg = _read(hooks, str(junk))
+    assert rc >= 1000 and "invalid format of matrix value" in msg
+    # mminfo's own codes (mmio.f:413-583)
+    for text, code in (("%%NotMatrixMarket matrix coordinate real symmetric\n1 1 1\n", 7),
+                       ("%%MatrixMarket tensor coordinate real symmetric\n1 1 1\n", 1),
+                       ("%%MatrixMarket matrix sparse real symmetric\n1 1 1\n", 8),
+                       ("%%MatrixMarket matrix coordinate quaternion symmetric\n1 1 1\n", 9),
+                       ("%%MatrixMarket matrix coordinate real diagonal\n1 1 1\n", 11),
+                       ("%%MatrixMarket matrix coordinate real symmetric\n3 3\n", 6),
+                       ("%%MatrixMarket matrix coordinate real symmetric\n% only comments\n", 4)):
+        p = tmp_path / "hdr.mtx"
+        p.write_text(text)
+        rc, _, _, _, _ = _read(hooks, str(p), with_body=False)
+        assert rc == code, (text, rc)
+    rc, _, _, _, _ = _read(hooks, str(tmp_path / "missing.mtx"), with_body=False)
+    assert rc != 0
+
+
+def test_printed_vecs_ranges_parser(hooks):
+    out = (ctypes.c_longlong * 400)()
+    msg = ctypes.create_string_buffer(256)
+    for spec in ("3", "1-4", "1-4,7,9-12", "5,6"):
+        n = hooks.ekapp_parse_ranges(spec.encode(), out, 200, msg, 256)
+        assert [(out[2 * i], out[2 * i + 1]) for i in range(n)] == app_io.parse_printed_vecs_ranges(spec)
+    assert hooks.ekapp_parse_ranges(b",3", out, 200, msg, 256) == -1 and b"invalid comma placement" in msg.value
+    assert hooks.ekapp_parse_ranges(b"-3", out, 200, msg, 256) == -1 and b"invalid hyphen placement" in msg.value
+    many = ",".join(str(i) for i in range(1, 102))
+    assert hooks.ekapp_parse_ranges(many.encode(), out, 200, msg, 256) == -1 and b"too many ranges" in msg.value
+
+
+def _run(args, cwd):
+    return subprocess.run([APP] + args, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
+
+
+def test_cli_dry_run_prints_the_reference_configuration_block(hooks, golden_dir, tmp_path):
+    fa, fb = (os.path.join(golden_dir, f"ELSES_MATRIX_BNZ30_{x}.mtx") for x in "AB")
+    r = _run(["-s", "general_b200", "-c", "-1", "--dry-run", fa, fb], tmp_path)
+    assert r.returncode == 0, r.stderr
+    out = r.stdout
+    for line in ("---------- Eigen Test start ----------", "----- Configurations -----", "problem type: generalized",
+                 f"matrix A file: {fa}", "matrix A field: real", "matrix A symm: symmetric", "matrix A rows: 30",
+                 "matrix B entries: 303", "solver: general_b200", "eigenvalues output file: eigenvalues.dat",
+                 "ipratios output file: ipratios.dat", "required eigenpairs: 30", "verified eigenpairs: 30",
+                 "log output file: log.json", "MPI processes: 1", "dry run mode, exit"):
+        assert line in out, line
+    assert "[Event" in r.stderr and "main:read_matrix_files" in r.stderr
+    assert not os.path.exists(tmp_path / "eigenvalues.dat")
+
+
+def test_cli_forked_ranks_dry_run(hooks, golden_dir, tmp_path):
+    """--ngpu P forks the ranks before CUDA is touched; only the master prints (check_master)."""
+    fa = os.path.join(golden_dir, "ELSES_MATRIX_VCNT400std_A.mtx")
+    r = _run(["-s", "b200", "--ngpu", "2", "--dry-run", fa], tmp_path)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.count("Eigen Test start") == 1 and "MPI processes: 2" in r.stdout
+
+
+@pytest.mark.parametrize("args,code,needle", [
+    (["-s", "nope", "A"], 1, "[Error] validate_argument: Unknown solver 'nope'"),
+    (["-s", "b200", "A", "B"], 1, "[Error] validate_argument: solver 'b200' is not for generalized eigenvalue problem"),
+    (["-s", "general_b200", "A"], 1, "[Error] validate_argument: solver 'general_b200' is not for standard eigenvalue problem"),
+    (["-s", "general_b200", "-n", "3", "A", "B"], 1, "does not support partial eigenvalue computation"),
+    (["-s", "general_scalapack", "A", "B"], 1, "is not supported in this build"),
+    (["-s", "general_b200", "-c", "31", "A", "B"], 1, "Specified numbers with -c option are not valid"),
+    (["-s", "general_b200", "-t", "5", "A", "B"], 1, "wrong format for -t option"),
+    (["-s", "general_b200", "-t", "5,31", "A", "B"], 1, "Specified numbers with -t option are not valid"),
+    (["-s", "general_b200", "-p", "1-31", "A", "B"], 1, "Specified numbers with -p option are not valid"),
+    (["-s", "general_b200", "-z", "A", "B"], 1, "[Error] read_command_argument: unknown option-z"),
+    (["-s", "general_b200"], 1, "[Error] read_command_argument: Matrix A file not specified"),
+    (["-h"], 0, "[Info] read_command_argument: help printed"),
+    (["-s", "b200", "missing.mtx"], None, "[Error] mminfo missing.mtx failed"),
+])
+def test_cli_error_behaviour_follows_terminate(hooks, golden_dir, tmp_path, args, code, needle):
+    fa, fb = (os.path.join(golden_dir, f"ELSES_MATRIX_BNZ30_{x}.mtx") for x in "AB")
+    args = [fa if a == "A" else fb if a == "B" else a for a in args]
+    r = _run(args + ["--dry-run"], tmp_path)
+    if code is None:
+        assert r.returncode != 0
+    else:
+        assert r.returncode == code
+    assert needle in r.stderr, r.stderr
+    if "-h" in args:
+        assert "Usage: eigen_test -s <solver_type> <options> <matrix_A> [<matrix_B>]" in r.stdout
+
+
+def test_cli_synthetic_spec_and_dimension_mismatch(hooks, golden_dir, tmp_path):
+    r = _run(["-s", "general_b200", "--dry-run", "synthetic:512:20240601", "synthetic:512:20240602"], tmp_path)
+    assert r.returncode == 0 and "matrix A rows: 512" in r.stdout and "required eigenpairs: 512" in r.stdout
+    r = _run(["-s", "general_b200", "--dry-run", "synthetic:512:1", "synthetic:256:2"], tmp_path)
+    assert r.returncode == 1 and "Matrix dimension mismatch" in r.stderr
+
+
+def test_cli_solver_call_fails_loudly_without_a_gpu(hooks, golden_dir, tmp_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    fa, fb = (os.path.join(golden_dir, f"ELSES_MATRIX_BNZ30_{x}.mtx") for x in "AB")
+    r = _run(["-s", "general_b200", fa, fb], tmp_path)
+    assert r.returncode != 0
+    assert "[Error] solver_b200: no usable CUDA device (there is no CPU fallback)" in r.stderr
+    assert " main:read_matrix_files" in r.stdout          # terminate prints the events first (processes.f90:128-131)
+    assert not os.path.exists(tmp_path / "eigenvalues.dat")
