@@ -53,6 +53,7 @@ _SIGS = {
     "ekb200_sy2sb_num_panels": [c_void_p, c_int64],
     "ekb200_get_band": [c_void_p],
     "ekb200_stedc": [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, POINTER(c_double)],
+    "ekb200_stebz_stein": [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64],
     "ekb200_sb2st": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p],
     "ekb200_sb2st_max_tasks": [c_void_p, c_int64],
     "ekb200_apply_q2": [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64],

@@ -108,6 +108,11 @@ int ekb200_set_option(ekb200_ctx* h, const char* key, int64_t value) {
     ctx->band = (int)value;
     return 0;
   }
+  if (!strcmp(key, "select_method")) {  // -n solvers: 0 auto | 1 divide and conquer | 2 bisection + inverse iteration
+    if (value < 0 || value > 2) return -3;
+    ctx->select_method = (int)value;
+    return 0;
+  }
   if (!strcmp(key, "reduction")) {  // 0: blocked pdsygst-style reduction (default); 1: explicit inverse of L
     if (value != 0 && value != 1) return -3;
     ctx->reduction = (int)value;
@@ -331,6 +336,25 @@ int ekb200_stedc(ekb200_ctx* h, int64_t n, double* d, double* e, double* w, doub
   void* work = nullptr;
   EKB_TRY(ctx_alloc(ctx, &work, stedc_workspace_bytes(n)));
   int rc = stedc(ctx, n, d, e, w, Z, ldz, work, merge_flops, 0, n);
+  cudaError_t ce = cudaStreamSynchronize(ctx->stream);
+  ctx_free(ctx, work);
+  if (rc == 0) EKB_CUDA(ce);
+  return rc;
+}
+
+int ekb200_stebz_stein(ekb200_ctx* h, int64_t n, int64_t nev, const double* d, const double* e, double* w, double* Z,
+                       int64_t ldz) {
+  CHECK_CTX(h);
+  if (n < 0) return -2;
+  if (nev < 0 || nev > n) return -3;
+  if (n > 0 && (!d || (n > 1 && !e))) return -4;
+  if (n > 0 && !w) return -6;
+  if (nev > 0 && !Z) return -7;
+  if (ldz < n) return -8;
+  if (n == 0) return 0;
+  void* work = nullptr;
+  EKB_TRY(ctx_alloc(ctx, &work, stebz_stein_workspace_bytes(n, ctx->num_sms)));
+  int rc = stebz_stein(ctx, n, d, e, w, nev, 0, nev, Z, ldz, work);
   cudaError_t ce = cudaStreamSynchronize(ctx->stream);
   ctx_free(ctx, work);
   if (rc == 0) EKB_CUDA(ce);

@@ -45,6 +45,7 @@ struct Ctx {
   int* h_info = nullptr;              // pinned mirror
   // options
   int band = 64;                      // b: half bandwidth of the two-stage reduction
+  int select_method = 0;              // -n solvers: 0 auto (D&C unless its workspaces do not fit), 1 D&C, 2 bisection + inverse iteration
   int reduction = 0;                  // 0: blocked pdsygst-style reduction; 1: explicit inverse (ELPA-style)
   int q2_kc = 0;                      // columns of Z per CTA in apply_q2 (0 = choose; 64|80|96|112|128)
   // stage timers
@@ -129,7 +130,7 @@ int gemm_profile_collect(Ctx* ctx, double* seconds, double* flops, long long* la
 // Per-launch CUDA-event brackets in "profile_gemm" mode, tagged by kernel family (roofline evidence measured
 // live inside bench.py).  prof_begin/prof_end are no-ops when profiling is off.
 enum ProfFamily { PROF_GEMM = 0, PROF_PANEL_QR = 1, PROF_Q2_APPLY = 2, PROF_SB2ST = 3, PROF_GEMM_BATCHED = 4,
-                  PROF_NCCL = 5, PROF_FAMILIES = 8 };
+                  PROF_NCCL = 5, PROF_STEBZ = 6 /* Sturm steps */, PROF_STEIN = 7 /* bytes */, PROF_FAMILIES = 8 };
 int prof_begin(Ctx* ctx, int family, double work);
 int prof_end(Ctx* ctx);
 int profile_collect(Ctx* ctx, double* seconds /*[PROF_FAMILIES]*/, double* work, long long* launches);
@@ -178,6 +179,11 @@ size_t stedc_workspace_bytes(i64 n);
 // (all of them for col_lo = 0, col_hi = n); the other columns of Z are left undefined.
 int stedc(Ctx* ctx, i64 n, double* d, double* e, double* w, double* Z, i64 ldz, void* work, double* flops_out,
           i64 col_lo, i64 col_hi);
+// bisection + inverse iteration (stebz.cu): all n eigenvalues into w, eigenvector columns [col_lo, col_hi) of the nev
+// lowest into Z(:, col_lo..col_hi); returns the number of vectors that failed dstein's growth test
+size_t stebz_stein_workspace_bytes(i64 n, int num_sms);
+int stebz_stein(Ctx* ctx, i64 n, const double* d, const double* e, double* w, i64 nev, i64 col_lo, i64 col_hi, double* Z,
+                i64 ldz, void* work);
 
 // ---------------------------------------------------------------- multi-GPU (dist.cu)
 int comm_unique_id(void* id128, std::string* err);

@@ -3,6 +3,10 @@
 // nothing on the solve path links this.
 #include "layout.h"
 #include "secular.cuh"
+#include "tridiag.cuh"
+#include <algorithm>
+#include <cmath>
+#include <vector>
 
 extern "C" int ekb200_host_secular(int k, const double* d, const double* z, double rho, double* lam, int* orig,
                                    double* tau, int* iters) {
@@ -24,4 +28,63 @@ extern "C" int ekb200_host_slab_bounds(long long ncols, int nranks, int gran, lo
   ekb::slab_bounds(ncols, nranks, gran, b);
   for (int r = 0; r <= nranks; ++r) bounds[r] = b[r];
   return 0;
+}
+
+// ---- bisection + inverse iteration (tridiag.cuh), the host run of exactly the code the CUDA kernels execute
+static void tri_setup(long long n, const double* d, const double* e, std::vector<double>& e2, double* gl, double* gu,
+                      double* onenrm, double* pivmin) {
+  e2.assign((size_t)n, 0.0);
+  double lo = d[0], hi = d[0], nrm = 0.0, emax2 = 0.0;
+  for (long long i = 0; i < n; ++i) {
+    const double l = i > 0 ? std::fabs(e[i - 1]) : 0.0, r = i + 1 < n ? std::fabs(e[i]) : 0.0;
+    lo = std::min(lo, d[i] - l - r);
+    hi = std::max(hi, d[i] + l + r);
+    nrm = std::max(nrm, std::fabs(d[i]) + l + r);
+    if (i + 1 < n) {
+      e2[i] = e[i] * e[i];
+      emax2 = std::max(emax2, e2[i]);
+    }
+  }
+  *pivmin = ekb::TRI_SAFMIN * std::max(1.0, emax2);
+  const double tnorm = std::max(std::fabs(lo), std::fabs(hi));
+  *gl = lo - 2.1 * tnorm * ekb::TRI_ULP * (double)n - 2.1 * *pivmin;
+  *gu = hi + 2.1 * tnorm * ekb::TRI_ULP * (double)n + 2.1 * *pivmin;
+  *onenrm = nrm;
+}
+
+extern "C" int ekb200_host_stebz(long long n, const double* d, const double* e, double* w, int* max_iters) {
+  std::vector<double> e2;
+  double gl, gu, onenrm, pivmin;
+  tri_setup(n, d, e, e2, &gl, &gu, &onenrm, &pivmin);
+  int mx = 0;
+  for (long long j = 0; j < n; ++j) {
+    int it = 0;
+    w[j] = ekb::bisect_index(n, d, e2.data(), j, gl, gu, pivmin, &it);
+    mx = std::max(mx, it);
+  }
+  if (max_iters) *max_iters = mx;
+  return 0;
+}
+
+// eigenvectors of w[0..nev) (ascending, as produced by ekb200_host_stebz); returns the number of failed vectors,
+// *nclusters / *max_cluster describe the clustering
+extern "C" int ekb200_host_stein(long long n, const double* d, const double* e, long long nev, const double* w, double* Z,
+                                 long long ldz, long long* nclusters, long long* max_cluster) {
+  std::vector<double> e2;
+  double gl, gu, onenrm, pivmin;
+  tri_setup(n, d, e, e2, &gl, &gu, &onenrm, &pivmin);
+  const double ortol = ekb::stein_ortol(nev, w, onenrm);
+  std::vector<long long> starts((size_t)nev + 2);
+  const long long nc = ekb::stein_clusters(0, nev, w, ortol, starts.data());
+  std::vector<double> ws((size_t)(4 * n + (n + 7) / 8 + 8));
+  ekb::HostTeam tm;
+  int fail = 0;
+  long long mc = 0;
+  for (long long c = 0; c < nc; ++c) {
+    ekb::stein_cluster(tm, n, d, e, w, starts[c], starts[c + 1], Z, ldz, 0, ws.data(), onenrm, &fail);
+    mc = std::max(mc, starts[c + 1] - starts[c]);
+  }
+  if (nclusters) *nclusters = nc;
+  if (max_cluster) *max_cluster = mc;
+  return fail;
 }

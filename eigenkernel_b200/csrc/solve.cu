@@ -83,7 +83,28 @@ int syevd_dev(Ctx* ctx, i64 n, i64 nev, double* A, i64 lda, double* w, double* Z
     if (rc) return rc;
   }
   sc.release(AB);
-  {
+  // Tridiagonal eigenproblem.  All pairs: divide and conquer (pdstedc).  The -n solvers may instead follow pdsyevx
+  // (bisection + inverse iteration, O(n k) memory): forced by option "select_method" = 2, and chosen automatically
+  // when the n x n workspaces of the D&C path do not fit next to A and the bulge-chasing reflectors (n = 65536).
+  bool use_stebz = false;
+  if (nev < n) {
+    if (ctx->select_method == 2) use_stebz = true;
+    else if (ctx->select_method == 0) {
+      size_t free_b = 0, total_b = 0;
+      EKB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+      const size_t need = stedc_workspace_bytes(n) + (size_t)round_up(n, 8) * n * sizeof(double);
+      use_stebz = need > free_b + ctx->cached_bytes;
+    }
+  }
+  if (use_stebz) {
+    StageTimer t(ctx, "eigen_solver_b200:stebz_stein");
+    void* work = nullptr;
+    EKB_TRY(sc.get(&work, stebz_stein_workspace_bytes(n, ctx->num_sms)));
+    int rc = stebz_stein(ctx, n, d, e, w, nev, c0, c0 + kc, Z, ldz, work);
+    t.stop();
+    sc.release(work);
+    if (rc) return rc;  // > 0: eigenvectors that failed to converge (IFAIL of pdsyevx)
+  } else {
     StageTimer t(ctx, "eigen_solver_b200:stedc");
     void* work = nullptr;
     EKB_TRY(sc.get(&work, stedc_workspace_bytes(n)));

@@ -31,6 +31,8 @@ const char* ekb200_strerror(int info);
 const char* ekb200_last_error(const ekb200_ctx* ctx);
 int ekb200_set_option(ekb200_ctx* ctx, const char* key, int64_t value); /* "band" = half bandwidth b (32|64); "profile_gemm" = 0|1;
                                                                            "cache_device_memory" = 1|0 (caching arena; 0 also trims);
+                                                                           "select_method" = 0 auto | 1 D&C | 2 bisection + inverse
+                                                                           iteration for the -n solvers;
                                                                            "reduction" = 0 blocked pdsygst-style | 1 explicit inverse of
                                                                            L (-s general_b200inv; solver_elpa_eigenexa.f90:110-150) */
 int ekb200_version(void);
@@ -100,6 +102,16 @@ int ekb200_get_band(const ekb200_ctx* ctx);
  *   merge GEMMs after deflation. */
 int ekb200_stedc(ekb200_ctx* ctx, int64_t n, double* dev_d, double* dev_e, double* dev_w, double* dev_Z, int64_t ldz,
                  double* merge_flops);
+
+/* ekb200_stebz_stein: the tridiagonal half of pdsyevx('V','I','L', il = 1, iu = nev, abstol = 2 safmin)
+ *   (solver_scalapack_select.f90:52-60), i.e. pdstebz + pdstein: bisection on the Sturm count, one eigenvalue per
+ *   thread, then inverse iteration, one cluster of close eigenvalues per warp (reorthogonalised inside the cluster).
+ *   dev_d (n), dev_e (n-1) are not modified.  dev_w (n) receives ALL eigenvalues ascending, dev_Z (n x nev) the
+ *   eigenvectors of the nev lowest.  O(n nev) memory.  info > 0: that many eigenvectors failed to converge (IFAIL).
+ *   The -n solvers use it instead of ekb200_stedc when option "select_method" = 2, or = 0 (auto) and the n x n
+ *   workspaces of the divide-and-conquer path do not fit (n = 65536 on one B200). */
+int ekb200_stebz_stein(ekb200_ctx* ctx, int64_t n, int64_t nev, const double* dev_d, const double* dev_e, double* dev_w,
+                       double* dev_Z, int64_t ldz);
 
 /* ekb200_apply_q2 / ekb200_apply_q1: the two halves of pdormtr('L','L','N') (solver_scalapack_all.f90:115-116):
  *   Z (n x nrhs) <- Q2 Z with the bulge-chasing reflectors of ekb200_sb2st, then Z <- Q1 Z with the panels
