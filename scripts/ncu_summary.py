@@ -36,7 +36,8 @@ def main(rep, out):
     if hi:
         hdr = rows[hi[0]]
         ix = {x: i for i, x in enumerate(hdr)}
-        data = [r for r in rows[hi[0] + 1:] if len(r) == len(hdr)]
+        stop = hi[1] if len(hi) > 1 else len(rows)   # several kernels in one report: the first kernel's listing only
+        data = [r for r in rows[hi[0] + 1:stop] if len(r) == len(hdr) and r != hdr]
         cls = {}
         for r in data:
             src = r[ix["Source"]].strip()
