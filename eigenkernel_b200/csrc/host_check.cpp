@@ -52,6 +52,23 @@ static void tri_setup(long long n, const double* d, const double* e, std::vector
   *onenrm = nrm;
 }
 
+// sections = 1 (plain bisection), 3 or 7 interior points per sweep: the variants the CUDA kernel instantiates
+extern "C" int ekb200_host_stebz_k(long long n, const double* d, const double* e, int sections, double* w, int* max_iters) {
+  std::vector<double> e2;
+  double gl, gu, onenrm, pivmin;
+  tri_setup(n, d, e, e2, &gl, &gu, &onenrm, &pivmin);
+  int mx = 0;
+  for (long long j = 0; j < n; ++j) {
+    int it = 0;
+    w[j] = sections == 7   ? ekb::bisect_index_k<7>(n, d, e2.data(), j, gl, gu, pivmin, &it)
+           : sections == 3 ? ekb::bisect_index_k<3>(n, d, e2.data(), j, gl, gu, pivmin, &it)
+                           : ekb::bisect_index_k<1>(n, d, e2.data(), j, gl, gu, pivmin, &it);
+    mx = std::max(mx, it);
+  }
+  if (max_iters) *max_iters = mx;
+  return 0;
+}
+
 extern "C" int ekb200_host_stebz(long long n, const double* d, const double* e, double* w, int* max_iters) {
   std::vector<double> e2;
   double gl, gu, onenrm, pivmin;

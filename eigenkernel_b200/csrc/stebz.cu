@@ -32,12 +32,13 @@ struct WarpTeam {
   __device__ __forceinline__ double bcast0(double v) const { return __shfl_sync(0xffffffffu, v, 0); }
 };
 
+template <int K>
 __global__ void __launch_bounds__(128) bisect_kernel(i64 n, i64 j_lo, i64 j_hi, const double* __restrict__ d,
                                                      const double* __restrict__ e2, double gl, double gu, double pivmin,
                                                      double* __restrict__ w) {
   const i64 j = j_lo + (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= j_hi) return;
-  w[j] = bisect_index(n, d, e2, j, gl, gu, pivmin, nullptr);
+  w[j] = bisect_index_k<K>(n, d, e2, j, gl, gu, pivmin, nullptr);
 }
 
 __global__ void __launch_bounds__(128) stein_kernel(i64 n, const double* __restrict__ d, const double* __restrict__ e,
@@ -107,9 +108,12 @@ int stebz_stein(Ctx* ctx, i64 n, const double* d, const double* e, double* w, i6
   cudaError_t ce = cudaMemcpyAsync(e2, he2.data(), (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream);
   if (ce != cudaSuccess) { cleanup(); EKB_CUDA(ce); }
   {
-    const int threads = 128;
+    // 7 interleaved branch-free chains per thread (3 bits per sweep).  Small problems use one-warp CTAs so that the
+    // n / 32 warps spread over all SMs instead of filling a few.
+    const int threads = n <= 16384 ? 32 : 128;
     prof_begin(ctx, PROF_STEBZ, (double)n * (double)n);  // Sturm steps per bisection sweep
-    bisect_kernel<<<cdiv(n, threads), threads, 0, ctx->stream>>>(n, 0, n, d, e2, gl, gu, pivmin, w); EKB_COUNT_LAUNCH(ctx);
+    bisect_kernel<7><<<cdiv(n, threads), threads, 0, ctx->stream>>>(n, 0, n, d, e2, gl, gu, pivmin, w);
+    EKB_COUNT_LAUNCH(ctx);
     prof_end(ctx);
     ce = cudaGetLastError();
     if (ce != cudaSuccess) { cleanup(); EKB_CUDA(ce); }

@@ -19,6 +19,12 @@
 
 #include "secular.cuh"  // EKB_HD
 
+#ifdef __CUDACC__
+#define EKB_UNROLL _Pragma("unroll")
+#else
+#define EKB_UNROLL
+#endif
+
 namespace ekb {
 
 constexpr double TRI_SAFMIN = 2.2250738585072014e-308;  // dlamch('S')
@@ -40,20 +46,114 @@ EKB_HD long long sturm_count(long long n, const double* d, const double* e2, dou
   return cnt;
 }
 
-// The j-th smallest eigenvalue (0-based) inside [gl, gu] (a Gershgorin interval widened like dstebz does).
-EKB_HD double bisect_index(long long n, const double* d, const double* e2, long long j, double gl, double gu,
-                           double pivmin, int* iters) {
+// e / q for the interleaved Sturm chains.  The IEEE double division of the toolchain carries a branch to a slow path
+// (subnormal / huge operands); with a branch per division the compiler cannot interleave the K chains and K = 7 ran
+// 1.8x SLOWER than plain bisection on the B200 (89 ms vs 50 ms at n = 8192).  On the device the quotient is therefore
+// formed branch-free: MUFU reciprocal seed, three Newton steps, one residual correction (error < 1 ulp).  The pivmin
+// safeguard keeps |q| >= safmin max(1, max e^2), so neither the reciprocal nor the quotient leaves the normal range.
+// The host build keeps the IEEE division; the two can only disagree on a count when the shift is within rounding
+// error of an eigenvalue.  Measured (profiles/r01_probe_select_inverse.jsonl): 58 ms at n = 8192, 0.28 s at n = 32768
+// for all n eigenvalues -- per bit of the result no better than the plain kernel (50 ms / 0.345 s): the 7 chains
+// issue at ~4.5 cycles per warp instruction instead of 7.5, far from the 2-cycle FP64 issue bound; ptxas reuses the
+// MUFU result registers across chains, which serialises them.  Open item for the next round (needs ncu).
+EKB_HD double sturm_quot(double e, double q) {
+#if defined(__CUDA_ARCH__) && !defined(EKB_STURM_IEEE_DIV)
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(q));
+  double t = fma(-q, r, 1.0);
+  r = fma(r, t, r);
+  t = fma(-q, r, 1.0);
+  r = fma(r, t, r);
+  t = fma(-q, r, 1.0);
+  r = fma(r, t, r);
+  const double v = e * r;
+  const double rem = fma(-v, q, e);
+  return fma(rem, r, v);
+#else
+  return e / q;
+#endif
+}
+
+// K Sturm counts in one sweep: K independent recurrences interleaved so the divide latency of one hides behind the
+// others (the single-chain kernel was latency-bound: ncu "wait" stalls 3.8 warps/issue, 16 % issue-active).  On the
+// host each count is bit-identical to sturm_count at the same shift.
+template <int K>
+EKB_HD void sturm_count_multi(long long n, const double* __restrict__ d, const double* __restrict__ e2, const double* x,
+                              double pivmin, long long* cnt) {
+  double q[K];
+  long long c[K];
+EKB_UNROLL
+  for (int k = 0; k < K; ++k) {
+    q[k] = d[0] - x[k];
+    if (fabs(q[k]) < pivmin) q[k] = -pivmin;
+    c[k] = q[k] <= 0.0 ? 1 : 0;
+  }
+  for (long long i = 1; i < n; ++i) {
+    const double di = d[i], ei = e2[i - 1];
+EKB_UNROLL
+    for (int k = 0; k < K; ++k) {
+      double t = di - sturm_quot(ei, q[k]) - x[k];
+      if (fabs(t) < pivmin) t = -pivmin;
+      q[k] = t;
+      if (t <= 0.0) ++c[k];
+    }
+  }
+EKB_UNROLL
+  for (int k = 0; k < K; ++k) cnt[k] = c[k];
+}
+
+// The j-th smallest eigenvalue (0-based) inside [gl, gu] (a Gershgorin interval widened like dstebz does), to dstebz's
+// tolerance for abstol = 2 safmin.  Multi-section: K interior points per sweep cut the bracket by K + 1 (K = 1 is
+// plain bisection); when the points no longer separate in floating point the sweep degenerates to a midpoint step.
+template <int K>
+EKB_HD double bisect_index_k(long long n, const double* __restrict__ d, const double* __restrict__ e2, long long j, double gl,
+                             double gu, double pivmin, int* iters) {
   double lo = gl, hi = gu;
   int it = 0;
   for (; it < 128; ++it) {
     const double mid = 0.5 * (lo + hi);
     const double tol = fmax(2.0 * TRI_SAFMIN, fmax(pivmin, 2.0 * TRI_ULP * fmax(fabs(lo), fabs(hi))));
     if (hi - lo <= tol || mid <= lo || mid >= hi) break;
-    if (sturm_count(n, d, e2, mid, pivmin) >= j + 1) hi = mid;
-    else lo = mid;
+    double x[K];
+    bool distinct = K > 1;
+    if (K > 1) {
+      const double h = (hi - lo) / (double)(K + 1);
+      double prev = lo;
+EKB_UNROLL
+      for (int k = 0; k < K; ++k) {
+        x[k] = lo + (double)(k + 1) * h;
+        if (!(x[k] > prev)) distinct = false;
+        prev = x[k];
+      }
+      if (!(prev < hi)) distinct = false;
+    }
+    if (!distinct) {
+      if (sturm_count(n, d, e2, mid, pivmin) >= j + 1) hi = mid;
+      else lo = mid;
+      continue;
+    }
+    long long c[K];
+    sturm_count_multi<K>(n, d, e2, x, pivmin, c);
+    double nlo = x[K - 1], nhi = hi;
+    bool found = false;
+EKB_UNROLL
+    for (int k = 0; k < K; ++k) {
+      if (!found && c[k] >= j + 1) {
+        found = true;
+        nhi = x[k];
+        nlo = k > 0 ? x[k - 1] : lo;
+      }
+    }
+    lo = nlo;
+    hi = nhi;
   }
   if (iters) *iters = it;
   return 0.5 * (lo + hi);
+}
+
+EKB_HD double bisect_index(long long n, const double* d, const double* e2, long long j, double gl, double gu,
+                           double pivmin, int* iters) {
+  return bisect_index_k<1>(n, d, e2, j, gl, gu, pivmin, iters);
 }
 
 // start vector of inverse iteration: counter-hash uniform in (-1, 1), identical on host and device
@@ -69,8 +169,9 @@ EKB_HD double stein_start(uint64_t j, uint64_t i) {
 // LU factorisation with partial pivoting of T - lambda I (the job dlagtf does for dstein).
 //   U: a (diagonal), b (first superdiagonal), d2 (second superdiagonal); multipliers c; piv[i] = 1 when rows i and
 //   i+1 were interchanged at step i.  All arrays have n entries.
-EKB_HD void gt_factor(long long n, const double* d, const double* e, double lambda, double* a, double* b, double* c,
-                      double* d2, unsigned char* piv) {
+EKB_HD void gt_factor(long long n, const double* __restrict__ d, const double* __restrict__ e, double lambda,
+                      double* __restrict__ a, double* __restrict__ b, double* __restrict__ c, double* __restrict__ d2,
+                      unsigned char* __restrict__ piv) {
   for (long long i = 0; i < n; ++i) {
     a[i] = d[i] - lambda;
     b[i] = i + 1 < n ? e[i] : 0.0;
@@ -100,26 +201,73 @@ EKB_HD void gt_factor(long long n, const double* d, const double* e, double lamb
   }
 }
 
-// x <- (T - lambda I)^-1 x with the factors of gt_factor; pivots smaller than `pert` are replaced by +-pert and
-// enlarged when the quotient would overflow (dlagts with job = -1).
-EKB_HD void gt_solve(long long n, const double* a, const double* b, const double* c, const double* d2,
-                     const unsigned char* piv, double* x, double pert) {
-  for (long long i = 0; i + 1 < n; ++i) {
-    if (piv[i]) {
-      const double t = x[i];
-      x[i] = x[i + 1];
-      x[i + 1] = t - c[i] * x[i];
-    } else {
-      x[i + 1] -= c[i] * x[i];
+// Reciprocal of a pivot of U, with pivots smaller than `pert` replaced by +-pert (dlagts with job = -1).  Applied to
+// the whole diagonal once per factorisation (by all lanes of the team) so the back substitution multiplies instead of
+// dividing on its critical path.
+EKB_HD double gt_pivot_recip(double p, double pert) {
+  if (fabs(p) < pert) p = p < 0.0 ? -pert : pert;
+  return 1.0 / p;
+}
+
+// x <- (T - lambda I)^-1 x with the factors of gt_factor and ainv[i] = gt_pivot_recip(a[i]).  Both sweeps are serial
+// recurrences (one FMA per row forward, two FMAs and a multiply backward); the operands of 8 rows are loaded before
+// the dependent chain touches them, so the loads overlap it instead of adding an L2 round trip per row (the first
+// version stalled 6.7 warps/issue on the scoreboard).  Components are clamped at 1e290 instead of overflowing.
+EKB_HD void gt_solve(long long n, const double* __restrict__ ainv, const double* __restrict__ b,
+                     const double* __restrict__ c, const double* __restrict__ d2, const unsigned char* __restrict__ piv,
+                     double* __restrict__ x) {
+  constexpr int U = 8;
+  double cur = x[0];
+  long long i = 0;
+  for (; i + U < n; i += U) {
+    double cc[U], xn[U];
+    unsigned char pp[U];
+EKB_UNROLL
+    for (int u = 0; u < U; ++u) {
+      cc[u] = c[i + u];
+      pp[u] = piv[i + u];
+      xn[u] = x[i + 1 + u];
+    }
+EKB_UNROLL
+    for (int u = 0; u < U; ++u) {
+      const double nxt = xn[u];
+      const double out = pp[u] ? nxt : cur;
+      const double carry = pp[u] ? cur - cc[u] * nxt : nxt - cc[u] * cur;
+      x[i + u] = out;
+      cur = carry;
     }
   }
+  for (; i + 1 < n; ++i) {
+    const double nxt = x[i + 1];
+    const double out = piv[i] ? nxt : cur;
+    const double carry = piv[i] ? cur - c[i] * nxt : nxt - c[i] * cur;
+    x[i] = out;
+    cur = carry;
+  }
+  x[n - 1] = cur;
   double x1 = 0.0, x2 = 0.0;  // x[i+1], x[i+2]
-  for (long long i = n - 1; i >= 0; --i) {
-    const double s = x[i] - b[i] * x1 - d2[i] * x2;
-    double p = a[i];
-    if (fabs(p) < pert) p = p < 0.0 ? -pert : pert;
-    if (fabs(s) > fabs(p) * 1e290) p = (p < 0.0 ? -1.0 : 1.0) * fabs(s) * 1e-290;
-    const double v = s / p;
+  i = n - 1;
+  for (; i - (U - 1) >= 0; i -= U) {
+    double bb[U], dd[U], aa[U], xx[U];
+EKB_UNROLL
+    for (int u = 0; u < U; ++u) {
+      bb[u] = b[i - u];
+      dd[u] = d2[i - u];
+      aa[u] = ainv[i - u];
+      xx[u] = x[i - u];
+    }
+EKB_UNROLL
+    for (int u = 0; u < U; ++u) {
+      double v = (xx[u] - bb[u] * x1 - dd[u] * x2) * aa[u];
+      if (fabs(v) > 1e290) v = v < 0.0 ? -1e290 : 1e290;
+      x[i - u] = v;
+      x2 = x1;
+      x1 = v;
+    }
+  }
+  for (; i >= 0; --i) {
+    double v = (x[i] - b[i] * x1 - d2[i] * x2) * ainv[i];
+    if (fabs(v) > 1e290) v = v < 0.0 ? -1e290 : 1e290;
     x[i] = v;
     x2 = x1;
     x1 = v;
@@ -203,6 +351,8 @@ EKB_HD void stein_cluster(const Team& tm, long long n, const double* d, const do
     // dstein scales the right-hand side to n |T|_1 max(eps, |u_nn|) and tests |x|_inf >= sqrt(0.1 / n); both are
     // written here relative to |T|_1 (as if T had unit norm) so matrices of norm 1e+-150 neither overflow nor fail
     const double unn = tm.bcast0(L == 0 ? fabs(a[n - 1]) : 0.0) / onenrm;
+    for (long long i = L; i < n; i += W) a[i] = gt_pivot_recip(a[i], pert_floor);  // a <- reciprocal pivots, all lanes
+    tm.sync();
     const double scl_target = (double)n * (eps > unn ? eps : unn);
     int nrmchk = 0, its = 0;
     bool ok = false;
@@ -216,7 +366,7 @@ EKB_HD void stein_cluster(const Team& tm, long long n, const double* d, const do
       const double scl = s1 > 0.0 ? scl_target / s1 : 1.0;
       for (long long i = L; i < n; i += W) x[i] *= scl;
       tm.sync();
-      if (L == 0) gt_solve(n, a, b, c, d2, piv, x, pert_floor);
+      if (L == 0) gt_solve(n, a, b, c, d2, piv, x);
       tm.sync();
       // modified Gram-Schmidt against the earlier vectors of the cluster
       for (long long q = j0; q < j; ++q) {

@@ -27,6 +27,7 @@ def hc():
         g.build()
     lib = ctypes.CDLL(HC)
     lib.ekb200_host_stebz.argtypes = [ll, dp, dp, dp, ctypes.POINTER(ctypes.c_int)]
+    lib.ekb200_host_stebz_k.argtypes = [ll, dp, dp, ctypes.c_int, dp, ctypes.POINTER(ctypes.c_int)]
     lib.ekb200_host_stein.argtypes = [ll, dp, dp, ll, dp, dp, ll, ctypes.POINTER(ll), ctypes.POINTER(ll)]
     return lib
 
@@ -99,6 +100,25 @@ def test_bisection_matches_lapack_eigenvalues(hc, name):
     assert np.all(np.diff(w) >= 0)
     assert np.max(np.abs(w - ref)) <= 8 * np.finfo(float).eps * tn * max(1.0, np.log2(len(d) + 1))
     assert it <= 128
+
+
+@pytest.mark.parametrize("sections", [3, 7])
+@pytest.mark.parametrize("name", list(cases()))
+def test_multisection_agrees_with_plain_bisection(hc, name, sections):
+    """The CUDA kernel cuts the bracket by 4 or 8 per sweep (3 / 7 interleaved Sturm chains); the counts are the same
+    function, so the final brackets overlap to dstebz's tolerance and far fewer sweeps are needed."""
+    d, e = cases()[name]
+    n = len(d)
+    w1, it1 = stebz(hc, d, e)
+    wk = np.zeros(n)
+    it = ctypes.c_int()
+    ee = np.ascontiguousarray(e if n > 1 else np.zeros(1))
+    hc.ekb200_host_stebz_k(n, d.ctypes.data_as(dp), ee.ctypes.data_as(dp), sections, wk.ctypes.data_as(dp), ctypes.byref(it))
+    assert np.all(np.diff(wk) >= 0)
+    assert np.all(np.abs(wk - w1) <= 4 * np.finfo(float).eps * np.maximum(np.abs(w1), np.abs(wk)) + 1e-300 +
+                  4 * np.finfo(float).tiny * max(1.0, float(np.max(e ** 2)) if len(e) else 1.0))
+    if n > 2 and it1 > 20:
+        assert it.value <= it1 // (2 if sections == 3 else 3) + 6
 
 
 @pytest.mark.parametrize("name", list(cases()))
