@@ -1,7 +1,7 @@
 """Host-side mirror of EigenKernel's solver boundary for the B200 solvers.
 
-`eigen_solver(arg, matrix_A, matrix_B)` is reference src/solver_main.f90:22-100 with four new cases
-(`b200`, `b200_select`, `general_b200`, `general_b200_select`) next to the existing names; the argument
+`eigen_solver(arg, matrix_A, matrix_B)` is reference src/solver_main.f90:22-100 with five new cases
+(`b200`, `b200_select`, `general_b200`, `general_b200_select`, `general_b200inv`) next to the existing names; the argument
 checks are `validate_argument` (src/command_argument.f90:121-219) extended by the same names; the result is
 the type-2 `eigenpairs` container of src/eigenpairs_types.f90:7-11 on a 1x1 grid (the local array IS the
 matrix).  All arithmetic happens in libekb200.so (hand-written CUDA); there is no CPU fallback: without the
@@ -22,7 +22,7 @@ G_BLOCK_SIZE = 64          # global_variables.f90:5
 G_VERSION = "20160808"     # global_variables.f90:6
 
 STANDARD_SOLVERS = ("b200", "b200_select")
-GENERALIZED_SOLVERS = ("general_b200", "general_b200_select")
+GENERALIZED_SOLVERS = ("general_b200", "general_b200_select", "general_b200inv")
 SELECT_SOLVERS = ("b200_select", "general_b200_select")
 # names of the reference that this build does not provide (they abort like the *_dummy.f90 twins)
 REFERENCE_ONLY_SOLVERS = (
@@ -142,6 +142,8 @@ def eigen_solver(arg: Argument, matrix_A: SparseMat, matrix_B: SparseMat | None 
             # g_block_size := --block-size (solver_main.f90:44-46); the device band width follows it when legal
             if arg.block_size in (32, 64):
                 ctx.set_option("band", arg.block_size)
+        # general_b200inv: explicit-inverse reduction (the ELPA-style workflow, solver_elpa_eigenexa.f90:110-150)
+        ctx.set_option("reduction", 1 if st == "general_b200inv" else 0)
         t0 = time.perf_counter()
         ijA, vA = _coo_ptrs(matrix_A)
         if generalized:

@@ -50,6 +50,12 @@ module ek_solver_b200_m
       real(c_double), intent(in) :: vA(*), vB(*)
       real(c_double), intent(out) :: w(*), Z(ldz, *)
     end function ekb200_sygvd_coo
+    integer(c_int) function ekb200_set_option(ctx, key, value) bind(C, name='ekb200_set_option')
+      import :: c_ptr, c_int, c_char, c_int64_t
+      type(c_ptr), value :: ctx
+      character(kind=c_char), intent(in) :: key(*)
+      integer(c_int64_t), value :: value
+    end function ekb200_set_option
     integer(c_int) function ekb200_device_count() bind(C, name='ekb200_device_count')
       import :: c_int
     end function ekb200_device_count
@@ -126,8 +132,9 @@ contains
   end subroutine replay_events
 
 
-  subroutine solve_b200_common(n, n_vec, proc, matrix_A, eigenpairs, matrix_B)
+  subroutine solve_b200_common(n, n_vec, proc, matrix_A, eigenpairs, matrix_B, reduction)
     integer, intent(in) :: n, n_vec
+    integer, intent(in), optional :: reduction  ! 0 blocked pdsygst-style (default), 1 explicit inverse (general_b200inv)
     type(ek_process_t), intent(in) :: proc
     type(ek_sparse_mat_t), intent(in) :: matrix_A
     type(ek_sparse_mat_t), intent(in), optional :: matrix_B
@@ -159,6 +166,11 @@ contains
       call mpi_bcast(nccl_id, 128, mpi_byte, 0, mpi_comm_world, ierr)
       info = ekb200_comm_init(ctx, int(proc%n_procs, c_int), int(proc%my_rank, c_int), nccl_id)
       if (info /= 0) call terminate('solver_b200: NCCL communicator could not be created', info)
+    end if
+
+    if (present(reduction)) then
+      info = ekb200_set_option(ctx, c_char_'reduction' // c_null_char, int(reduction, c_int64_t))
+      if (info /= 0) call terminate('solver_b200: option reduction rejected', info)
     end if
 
     eigenpairs%type_number = 2
@@ -212,12 +224,18 @@ contains
   end subroutine solve_with_b200
 
 
-  ! -s general_b200 / -s general_b200_select : generalized problem
-  subroutine solve_with_general_b200(n, n_vec, proc, matrix_A, eigenpairs, matrix_B)
+  ! -s general_b200 / -s general_b200_select : generalized problem;  -s general_b200inv passes reduction = 1, the
+  ! ELPA-style explicit-inverse workflow of solver_elpa_eigenexa.f90:110-150 (invert L, two products, TRMM recovery)
+  subroutine solve_with_general_b200(n, n_vec, proc, matrix_A, eigenpairs, matrix_B, reduction)
     integer, intent(in) :: n, n_vec
     type(ek_process_t), intent(in) :: proc
     type(ek_sparse_mat_t), intent(in) :: matrix_A, matrix_B
     type(ek_eigenpairs_types_union_t), intent(out) :: eigenpairs
-    call solve_b200_common(n, n_vec, proc, matrix_A, eigenpairs, matrix_B)
+    integer, intent(in), optional :: reduction
+    if (present(reduction)) then
+      call solve_b200_common(n, n_vec, proc, matrix_A, eigenpairs, matrix_B, reduction)
+    else
+      call solve_b200_common(n, n_vec, proc, matrix_A, eigenpairs, matrix_B)
+    end if
   end subroutine solve_with_general_b200
 end module ek_solver_b200_m

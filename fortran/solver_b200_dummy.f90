@@ -15,11 +15,12 @@ contains
     type(ek_eigenpairs_types_union_t), intent(out) :: eigenpairs
     call terminate('solver_b200: B200 solvers are not supported in this build', 1)
   end subroutine solve_with_b200
-  subroutine solve_with_general_b200(n, n_vec, proc, matrix_A, eigenpairs, matrix_B)
+  subroutine solve_with_general_b200(n, n_vec, proc, matrix_A, eigenpairs, matrix_B, reduction)
     integer, intent(in) :: n, n_vec
     type(ek_process_t), intent(in) :: proc
     type(ek_sparse_mat_t), intent(in) :: matrix_A, matrix_B
     type(ek_eigenpairs_types_union_t), intent(out) :: eigenpairs
+    integer, intent(in), optional :: reduction
     call terminate('solver_b200: B200 solvers are not supported in this build', 1)
   end subroutine solve_with_general_b200
 end module ek_solver_b200_m
