@@ -92,11 +92,13 @@ void launch_ranks(int nranks) {
   sa.sa_handler = on_sigchld;
   sa.sa_flags = SA_RESTART | SA_NOCLDSTOP;
   sigaction(SIGCHLD, &sa, nullptr);
+  const pid_t rank0 = getpid();
   for (int r = 1; r < nranks; ++r) {
     pid_t p = fork();
     if (p < 0) terminate("launch_ranks: fork failed", 1);
     if (p == 0) {
       prctl(PR_SET_PDEATHSIG, SIGKILL);  // a rank never outlives rank 0
+      if (getppid() != rank0) _exit(1);  // ... even if rank 0 died before the line above
       signal(SIGCHLD, SIG_DFL);
       s_num_children = 0;
       set_world(r, nranks);

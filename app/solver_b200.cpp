@@ -21,6 +21,7 @@ static ekb200_ctx* s_ctx = nullptr;
 // device-resident state of a synthetic run (kept for the verifier): full n x n_vec eigenvectors, eigenvalues
 static double *s_dev_Z = nullptr, *s_dev_w = nullptr;
 static int64_t s_dev_ldz = 0;
+static void* s_host_vectors = nullptr;  // pinned local piece of the eigenvector matrix (blacs%Vectors)
 
 static void check(int info, const char* routine) {
   if (info == 0) return;
@@ -66,6 +67,8 @@ void b200_finalize() {
   if (s_dev_Z) ekb200_dev_free(s_ctx, s_dev_Z);
   if (s_dev_w) ekb200_dev_free(s_ctx, s_dev_w);
   s_dev_Z = s_dev_w = nullptr;
+  if (s_host_vectors) ekb200_host_free(s_ctx, s_host_vectors);
+  s_host_vectors = nullptr;
   ekb200_destroy(s_ctx);
   s_ctx = nullptr;
 }
@@ -141,6 +144,8 @@ void solve_with_b200(const ek_argument_t& arg, int64_t n, const ek_process_t& pr
   void* host = nullptr;
   check(ekb200_host_alloc(ctx, (int64_t)sizeof(double) * ep.lld * (nloc > 0 ? nloc : 1), &host), "ekb200_host_alloc");
   ep.Vectors = (double*)host;
+  if (s_host_vectors) ekb200_host_free(ctx, s_host_vectors);
+  s_host_vectors = host;
 
   int info = 0;
   if (arg.matrix_A_info.synthetic) {
