@@ -90,10 +90,15 @@ int syevd_dev(Ctx* ctx, i64 n, i64 nev, double* A, i64 lda, double* w, double* Z
   if (nev < n) {
     if (ctx->select_method == 2) use_stebz = true;
     else if (ctx->select_method == 0) {
+      // decided from the device's TOTAL memory and a size-only estimate of what is live (A, the bulge-chasing
+      // reflectors, possibly the Cholesky factor, the eigenvector slab), never from the free memory of the moment:
+      // every rank of a sharded solve must take the same branch (replicated stages have to stay bit-identical)
       size_t free_b = 0, total_b = 0;
       EKB_CUDA(cudaMemGetInfo(&free_b, &total_b));
-      const size_t need = stedc_workspace_bytes(n) + (size_t)round_up(n, 8) * n * sizeof(double);
-      use_stebz = need > free_b + ctx->cached_bytes;
+      const double nn = (double)round_up(n, 8) * (double)n * sizeof(double);
+      const double live = 3.0 * nn + (double)round_up(n, 8) * (double)nev * sizeof(double);
+      const double need = (double)stedc_workspace_bytes(n) + nn;
+      use_stebz = live + need > 0.9 * (double)total_b;
     }
   }
   if (use_stebz) {
