@@ -18,23 +18,24 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
 __global__ void fill_synth_kernel(double* __restrict__ A, i64 lda, i64 n, uint64_t seed, double offdiag_div,
                                   int diag_mode, double diag_value) {
   i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-  i64 j = blockIdx.y;
   if (i >= n) return;
-  uint64_t hi = i > j ? i : j, lo = i > j ? j : i;
-  uint64_t z = splitmix64(seed ^ ((hi << 32) | lo));
-  double u = (double)(z >> 11) * 0x1.0p-52 - 1.0;
-  double v;
-  if (i == j)
-    v = diag_mode == 0 ? u + diag_value : diag_value;
-  else
-    v = u / offdiag_div;
-  A[j * lda + i] = v;
+  for (i64 j = blockIdx.y; j < n; j += gridDim.y) {  // gridDim.y is capped at 32768 (n = 65536 exceeds the 65535 limit)
+    uint64_t hi = i > j ? i : j, lo = i > j ? j : i;
+    uint64_t z = splitmix64(seed ^ ((hi << 32) | lo));
+    double u = (double)(z >> 11) * 0x1.0p-52 - 1.0;
+    double v;
+    if (i == j)
+      v = diag_mode == 0 ? u + diag_value : diag_value;
+    else
+      v = u / offdiag_div;
+    A[j * lda + i] = v;
+  }
 }
 
 int fill_synthetic(Ctx* ctx, double* A, i64 lda, i64 n, uint64_t seed, double offdiag_div, int diag_mode,
                    double diag_value) {
   if (n <= 0) return 0;
-  dim3 grid(cdiv(n, 256), (unsigned)n);
+  dim3 grid(cdiv(n, 256), (unsigned)(n < 32768 ? n : 32768));
   fill_synth_kernel<<<grid, 256, 0, ctx->stream>>>(A, lda, n, seed, offdiag_div, diag_mode, diag_value); EKB_COUNT_LAUNCH(ctx);
   EKB_CUDA(cudaGetLastError());
   return 0;
