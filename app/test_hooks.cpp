@@ -86,3 +86,31 @@ int ekapp_parse_ranges(const char* spec, long long* ranges, int cap, char* msg, 
   return num;
 }
 }
+
+// print_eigenvectors on a caller-provided n x k matrix (1 x 1 grid): files <dir>/<j:08d>.dat for j in ranges
+extern "C" int ekapp_print_eigenvectors(const char* dir, long long n, long long k, const double* X, long long ldx,
+                                        const char* ranges_spec, int binary, int threads, char* msg, int msgcap) {
+  set_world(1, 2);  // quiet
+  ek_argument_t arg;
+  arg.eigenvector_dir = dir;
+  arg.is_binary_output = binary != 0;
+  arg.io_threads = threads;
+  ek_eigenpairs_types_union_t ep;
+  ep.type_number = 2;
+  ep.blacs.desc[rows_] = n;
+  ep.blacs.desc[cols_] = k;
+  ep.blacs.Vectors = const_cast<double*>(X);
+  ep.blacs.lld = ldx;
+  ep.blacs.loc_cols = k;
+  ep.blacs.col0 = 0;
+  int rc = 0;
+  try {
+    arg_str_to_printed_vecs_ranges(ranges_spec, arg.num_printed_vecs_ranges, arg.printed_vecs_ranges);
+    print_eigenvectors(arg, ep);
+  } catch (const Terminate& t) {
+    put(t.message, msg, msgcap);
+    rc = 1000 + (t.code & 0xff);
+  }
+  set_world(0, 1);
+  return rc;
+}

@@ -173,6 +173,63 @@ def test_printed_vecs_ranges_parser(hooks):
     assert hooks.ekapp_parse_ranges(many.encode(), out, 200, msg, 256) == -1 and b"too many ranges" in msg.value
 
 
+def test_eigenvector_files_match_python_restatement(hooks, tmp_path):
+    """print_eigenvectors (matrix_io.f90:173-285): <dir>/<j:08d>.dat, text '(I8," ",I8," ",E26.16e3)' or one Fortran
+    unformatted record; the threaded writer produces the same bytes as the Python restatement."""
+    hooks.ekapp_print_eigenvectors.argtypes = [ctypes.c_char_p, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_void_p,
+                                               ctypes.c_longlong, ctypes.c_char_p, ctypes.c_int, ctypes.c_int,
+                                               ctypes.c_char_p, ctypes.c_int]
+    rng = np.random.default_rng(2)
+    n, k = 257, 12
+    X = np.asfortranarray(rng.standard_normal((n, k)) * 10.0 ** rng.integers(-200, 200, (n, k)))
+    msg = ctypes.create_string_buffer(256)
+    for binary, threads in ((0, 1), (0, 4), (1, 3)):
+        d = tmp_path / f"out_{binary}_{threads}"
+        d.mkdir()
+        rc = hooks.ekapp_print_eigenvectors(str(d).encode(), n, k, X.ctypes.data, n, b"1-3,7,12", binary, threads, msg, 256)
+        assert rc == 0, msg.value
+        assert sorted(os.listdir(d)) == [f"{j:08d}.dat" for j in (1, 2, 3, 7, 12)]
+        ref = tmp_path / f"ref_{binary}_{threads}"
+        ref.mkdir()
+        for j in (1, 2, 3, 7, 12):
+            app_io.write_eigenvector(str(ref), j, X[:, j - 1], binary=bool(binary))
+            assert open(d / f"{j:08d}.dat", "rb").read() == open(ref / f"{j:08d}.dat", "rb").read()
+    rc = hooks.ekapp_print_eigenvectors(str(tmp_path / "no_such_dir").encode(), n, k, X.ctypes.data, n, b"1", 0, 1, msg, 256)
+    assert rc >= 1000 and b"print_eigenvectors: cannot open" in msg.value
+
+
+def test_parser_fuzz_against_python_reader(hooks, tmp_path):
+    """Random small MatrixMarket files (mixed separators, signs, exponents, comment blocks): the C++ reader and the
+    Python restatement of read_matrix_file agree entry for entry."""
+    rng = np.random.default_rng(99)
+    for trial in range(40):
+        n = int(rng.integers(1, 40))
+        nnz = int(rng.integers(1, 3 * n + 2))
+        ii = rng.integers(1, n + 1, nnz)
+        jj = rng.integers(1, n + 1, nnz)
+        vv = rng.standard_normal(nnz) * 10.0 ** rng.integers(-30, 30, nnz)
+        p = tmp_path / f"f{trial}.mtx"
+        with open(p, "w") as f:
+            f.write("%%MatrixMarket matrix coordinate real symmetric\n")
+            for _ in range(int(rng.integers(0, 4))):
+                f.write("% comment line\n")
+            f.write(f" {n}  {n} {nnz}\n")
+            for i, j, v in zip(ii, jj, vv):
+                style = int(rng.integers(0, 4))
+                if style == 0:
+                    f.write(f"{i} {j} {v:.17g}\n")
+                elif style == 1:
+                    f.write(f"   {i}\t{j}   {v:+.16e}\n")
+                elif style == 2:
+                    f.write(f"{i} {j} " + f"{v:.16e}".replace("e", "D") + "\n")
+                else:
+                    f.write(f"{i} {j} {v:.17g}   \r\n")
+        rc, dims, ij, v, msg = _read(hooks, str(p), threads=int(rng.integers(1, 4)))
+        assert rc == 0, msg
+        ref = app_io.read_matrix_file(str(p))
+        assert dims == (n, n, nnz) and np.array_equal(ij, ref.suffix) and np.array_equal(v, ref.value)
+
+
 def _run(args, cwd):
     return subprocess.run([APP] + args, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
 
