@@ -110,3 +110,24 @@ def test_product_path_fails_loudly_without_gpu():
     from eigenkernel_b200._lib import Ekb200Error
     with pytest.raises(Ekb200Error):
         Context(0)
+
+
+def test_built_library_carries_the_blackwell_fp64_path():
+    """Static evidence (hard part 1): the sm_100a cubin uses the FP64 tensor path (DMMA.8x8x4), cp.async
+    pipelines (LDGSTS) and TMA bulk copies with mbarrier transactions (UBLKCP / SYNCS) -- and nothing was silently
+    compiled for another architecture."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__ as g
+        g.build()
+    elf = subprocess.run([cuobjdump, "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", elf))
+    assert archs == {"100a"}, archs
+    sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert sass.count("DMMA.8x8x4") > 1000
+    assert sass.count("LDGSTS") > 100
+    assert sass.count("UBLKCP") > 0 and sass.count("SYNCS.ARRIVE.TRANS") > 0
