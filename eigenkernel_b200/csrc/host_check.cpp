@@ -85,6 +85,25 @@ extern "C" int ekb200_host_stebz(long long n, const double* d, const double* e, 
 
 // eigenvectors of w[0..nev) (ascending, as produced by ekb200_host_stebz); returns the number of failed vectors,
 // *nclusters / *max_cluster describe the clustering
+// the same for a rank's column slab [col_lo, col_hi) of the nev requested vectors (Z: full n x nev buffer)
+extern "C" int ekb200_host_stein_slab(long long n, const double* d, const double* e, long long nev, const double* w,
+                                      long long col_lo, long long col_hi, double* Z, long long ldz) {
+  std::vector<double> e2;
+  double gl, gu, onenrm, pivmin;
+  tri_setup(n, d, e, e2, &gl, &gu, &onenrm, &pivmin);
+  const double ortol = ekb::stein_ortol(nev, w, onenrm);
+  std::vector<long long> starts((size_t)nev + 2);
+  const long long nc = ekb::stein_clusters(0, nev, w, ortol, starts.data());
+  long long first = 0, count = 0;
+  ekb::stein_cluster_range(nc, starts.data(), col_lo, col_hi, &first, &count);
+  std::vector<double> ws((size_t)(4 * n + (n + 7) / 8 + 8));
+  ekb::HostTeam tm;
+  int fail = 0;
+  for (long long c = first; c < first + count; ++c)
+    ekb::stein_cluster(tm, n, d, e, w, starts[c], starts[c + 1], Z, ldz, 0, ws.data(), onenrm, &fail);
+  return fail;
+}
+
 extern "C" int ekb200_host_stein(long long n, const double* d, const double* e, long long nev, const double* w, double* Z,
                                  long long ldz, long long* nclusters, long long* max_cluster) {
   std::vector<double> e2;

@@ -66,7 +66,8 @@ size_t stebz_stein_workspace_bytes(i64 n, int num_sms) {
 
 // d, e: the tridiagonal matrix on the device (not modified).  w (device, n): ALL eigenvalues ascending.  Z: columns
 // [col_lo, col_hi) of the eigenvector matrix of the nev lowest eigenvalues are written to Z(:, col_lo..col_hi) (the
-// caller's slab; Z is indexed by global column).  info > 0: number of vectors whose inverse iteration did not pass
+// caller's slab; Z is the full n x nev buffer indexed by global column -- clusters of close eigenvalues that straddle
+// the slab border are computed whole, which writes a few scratch columns outside the slab).  info > 0: number of vectors whose inverse iteration did not pass
 // dstein's growth test.
 int stebz_stein(Ctx* ctx, i64 n, const double* d, const double* e, double* w, i64 nev, i64 col_lo, i64 col_hi, double* Z,
                 i64 ldz, void* work) {
@@ -133,13 +134,16 @@ int stebz_stein(Ctx* ctx, i64 n, const double* d, const double* e, double* w, i6
     if (ce != cudaSuccess) { cleanup(); EKB_CUDA(ce); }
   }
   const double ortol = stein_ortol(nev, hw.data(), onenrm);
-  std::vector<i64> starts((size_t)(col_hi - col_lo) + 2);
-  const i64 nclusters = stein_clusters(col_lo, col_hi, hw.data(), ortol, (long long*)starts.data());
+  std::vector<i64> starts_all((size_t)nev + 2);
+  const i64 nc_all = stein_clusters(0, nev, hw.data(), ortol, (long long*)starts_all.data());
+  long long first = 0, nclusters = 0;
+  stein_cluster_range(nc_all, (const long long*)starts_all.data(), col_lo, col_hi, &first, &nclusters);
+  const i64* starts = starts_all.data() + first;  // the clusters that intersect this rank's slab, whole
   int rc = ctx_alloc(ctx, (void**)&d_starts, (size_t)(nclusters + 1) * sizeof(i64));
   if (!rc) rc = ctx_alloc(ctx, (void**)&d_fail, (size_t)(nclusters + 1) * sizeof(int));
   if (!rc) rc = ctx_alloc(ctx, (void**)&d_next, 64);
   if (rc) { cleanup(); return rc; }
-  ce = cudaMemcpyAsync(d_starts, starts.data(), (size_t)(nclusters + 1) * sizeof(i64), cudaMemcpyHostToDevice, ctx->stream);
+  ce = cudaMemcpyAsync(d_starts, starts, (size_t)(nclusters + 1) * sizeof(i64), cudaMemcpyHostToDevice, ctx->stream);
   if (ce == cudaSuccess) ce = cudaMemsetAsync(d_fail, 0, (size_t)(nclusters + 1) * sizeof(int), ctx->stream);
   if (ce == cudaSuccess) ce = cudaMemsetAsync(d_next, 0, 64, ctx->stream);
   if (ce != cudaSuccess) { cleanup(); EKB_CUDA(ce); }

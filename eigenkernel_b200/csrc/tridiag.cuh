@@ -304,6 +304,20 @@ inline long long stein_clusters(long long lo, long long hi, const double* w, dou
   return nc;
 }
 
+// Sharded solves: every rank cuts the clusters of ALL requested eigenvalues (same list everywhere) and processes the
+// ones that intersect its column slab [col_lo, col_hi) completely, so a cluster that straddles a slab border is
+// orthogonalised as a whole on both ranks (bit-identical: the per-cluster arithmetic has a fixed order) instead of
+// being cut at the border the way pdstein cuts at process borders.  Columns outside the slab are scratch.
+inline void stein_cluster_range(long long nc, const long long* starts, long long col_lo, long long col_hi,
+                                long long* first, long long* count) {
+  long long f = 0;
+  while (f < nc && starts[f + 1] <= col_lo) ++f;
+  long long l = f;
+  while (l < nc && starts[l] < col_hi) ++l;
+  *first = f;
+  *count = col_hi > col_lo ? l - f : 0;
+}
+
 // Team abstraction: on the device a warp (lane 0 runs the serial recurrences, all lanes the vector work), on the
 // host a single "lane".
 struct HostTeam {
