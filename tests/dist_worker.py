@@ -1,7 +1,7 @@
 """torchrun worker of the multi-GPU parity tests (one rank per B200):
 
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 \
-      tests/dist_worker.py [--cases small|full]
+      tests/dist_worker.py [--cases small|full|select] [--select-method 0|1|2]
 
 Every rank solves the same synthetic problem through the SAME C-ABI entry points as the single-GPU path, with
 the context attached to the NCCL ranks; rank 0 then checks (a) BASELINE.json's acceptance metrics against the
@@ -34,6 +34,7 @@ def main():
 
     ap = argparse.ArgumentParser()
     ap.add_argument("--cases", default="small")
+    ap.add_argument("--select-method", type=int, default=0, help="0 auto | 1 divide and conquer | 2 bisection + inverse iteration")
     args = ap.parse_args()
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -46,12 +47,17 @@ def main():
     ctx.lib.ekb200_comm_info(ctx.h, ctypes.byref(nr), ctypes.byref(rk))
     assert (nr.value, rk.value) == (world, rank)
     solo = Context(local)  # same GPU, no communicator: the single-GPU answer
+    ctx.set_option("select_method", args.select_method)
+    solo.set_option("select_method", args.select_method)
 
     # (n, nev, generalized, seed)
     cases = [(700, 700, True, 11), (1000, 1000, False, 12), (2048, 2048, True, 13), (1536, 200, True, 14),
              (1536, 300, False, 15)]
     if args.cases == "full":
         cases += [(4096, 4096, True, 16), (8192, 8192, True, 20240601)]
+    if args.cases == "select":  # the -n solvers only: slab borders inside the requested range, odd widths
+        cases = [(1536, 200, True, 14), (1536, 300, False, 15), (3000, 700, False, 17), (2000, 1999, True, 18),
+                 (900, 129, False, 19)]
     done = 0
     for n, nev, gen, seed in cases:
         if rank == 0:
