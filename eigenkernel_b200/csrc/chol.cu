@@ -100,7 +100,8 @@ __global__ void __launch_bounds__(64) trtri_blocks_kernel(const double* __restri
 
 int trtri_diag_blocks(Ctx* ctx, i64 n, const double* L, i64 ldl, double* invd) {
   if (n <= 0) return 0;
-  static bool attr = false;
+  static bool attr_dev[64] = {};  // per device: the attribute belongs to the device's context
+  bool& attr = attr_dev[ctx->device & 63];
   if (!attr) {
     EKB_CUDA(cudaFuncSetAttribute(trtri_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LEAF_SMEM));
     attr = true;
@@ -185,7 +186,8 @@ int trsm_lower(Ctx* ctx, int kind, i64 m, i64 n, const double* L, i64 ldl, const
 static int potrf_rec(Ctx* ctx, i64 n, double* A, i64 lda, double* invd, i64 goff, double* tmp) {
   if (n <= 0) return 0;
   if (n <= NB) {
-    static bool attr = false;
+    static bool attr_dev[64] = {};  // per device: the attribute belongs to the device's context
+    bool& attr = attr_dev[ctx->device & 63];
     if (!attr) {
       EKB_CUDA(cudaFuncSetAttribute(potrf_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LEAF_SMEM));
       attr = true;
@@ -338,7 +340,8 @@ static int sygst_rec(Ctx* ctx, i64 n, double* A, i64 lda, const double* L, i64 l
                      double* Mws) {
   if (n <= 0) return 0;
   if (n <= NB) {
-    static bool attr = false;
+    static bool attr_dev[64] = {};  // per device: the attribute belongs to the device's context
+    bool& attr = attr_dev[ctx->device & 63];
     constexpr size_t smem = 3 * NB * (NB + 1) * sizeof(double);
     if (!attr) {
       EKB_CUDA(cudaFuncSetAttribute(sygst_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

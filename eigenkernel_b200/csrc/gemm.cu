@@ -296,7 +296,8 @@ template <int BM, int BN, int WM, int WN, bool BATCHED>
 static int launch_cfg(Ctx* ctx, int flags, const GemmP& p, const GemmP* d_batch, int nb, int max_m, int max_n,
                       int tri_keep, int splitk) {
   constexpr size_t smem = (size_t)GEMM_STAGES * (BM + BN) * LDK * sizeof(double);
-  static bool attr_set = false;
+  static bool attr_dev[64] = {};  // per device: the attribute belongs to the device's context
+  bool& attr_set = attr_dev[ctx->device & 63];
   auto kern = gemm_kernel<BM, BN, WM, WN, BATCHED>;
   if (!attr_set) {
     EKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
