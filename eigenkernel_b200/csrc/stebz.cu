@@ -32,8 +32,12 @@ struct WarpTeam {
   __device__ __forceinline__ double bcast0(double v) const { return __shfl_sync(0xffffffffu, v, 0); }
 };
 
+// __launch_bounds__(128, 4): with no minimum-blocks hint ptxas schedules for the fewest registers (64) and re-serialises
+// the K chains that the source interleaves (seven Newton sequences back to back on shared temporaries: measured no
+// faster than plain bisection); with the hint it takes 88 registers and keeps K independent instructions between
+// dependent ones (checked in SASS: cuobjdump -sass, MUFU.RCP64H of the 7 chains within 30 instructions).
 template <int K>
-__global__ void __launch_bounds__(128) bisect_kernel(i64 n, i64 j_lo, i64 j_hi, const double* __restrict__ d,
+__global__ void __launch_bounds__(128, 4) bisect_kernel(i64 n, i64 j_lo, i64 j_hi, const double* __restrict__ d,
                                                      const double* __restrict__ e2, double gl, double gu, double pivmin,
                                                      double* __restrict__ w) {
   const i64 j = j_lo + (i64)blockIdx.x * blockDim.x + threadIdx.x;

@@ -53,9 +53,9 @@ EKB_HD long long sturm_count(long long n, const double* d, const double* e2, dou
 // safeguard keeps |q| >= safmin max(1, max e^2), so neither the reciprocal nor the quotient leaves the normal range.
 // The host build keeps the IEEE division; the two can only disagree on a count when the shift is within rounding
 // error of an eigenvalue.  Measured (profiles/r01_probe_select_inverse.jsonl): 58 ms at n = 8192, 0.28 s at n = 32768
-// for all n eigenvalues -- per bit of the result no better than the plain kernel (50 ms / 0.345 s): the 7 chains
-// issue at ~4.5 cycles per warp instruction instead of 7.5, far from the 2-cycle FP64 issue bound; ptxas reuses the
-// MUFU result registers across chains, which serialises them.  Open item for the next round (needs ncu).
+// for all n eigenvalues -- per bit of the result no better than the plain kernel (50 ms / 0.345 s): SASS showed why --
+// ptxas had re-serialised the 7 chains (one Newton sequence after the other on shared temporaries).  Fixed after
+// the measurement by stage-major source + a minimum-blocks launch bound (SASS now interleaved; not re-timed yet).
 EKB_HD double sturm_quot(double e, double q) {
 #if defined(__CUDA_ARCH__) && !defined(EKB_STURM_IEEE_DIV)
   double r;
@@ -74,15 +74,45 @@ EKB_HD double sturm_quot(double e, double q) {
 #endif
 }
 
+// v[k] = e / q[k] for K independent chains, written STAGE BY STAGE (all seeds, then every Newton step for all k, ...):
+// ptxas keeps the source order inside the loop body, and with the chains written one after the other it emitted seven
+// serial Newton sequences on shared temporaries (SASS of the first 7-chain kernel: no gain over plain bisection).
+// Stage-major source gives K independent instructions between two dependent ones in the PTX; ptxas keeps that order
+// only when the kernel carries a minimum-blocks launch bound (see bisect_kernel in stebz.cu).  Per chain the
+// operations and their order are exactly those of sturm_quot.
+template <int K>
+EKB_HD void sturm_quot_multi(double e, const double* q, double* v) {
+#if defined(__CUDA_ARCH__) && !defined(EKB_STURM_IEEE_DIV)
+  double r[K], t[K];
+  EKB_UNROLL
+  for (int k = 0; k < K; ++k) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r[k]) : "d"(q[k]));
+  EKB_UNROLL
+  for (int s = 0; s < 3; ++s) {
+    EKB_UNROLL
+    for (int k = 0; k < K; ++k) t[k] = fma(-q[k], r[k], 1.0);
+    EKB_UNROLL
+    for (int k = 0; k < K; ++k) r[k] = fma(r[k], t[k], r[k]);
+  }
+  EKB_UNROLL
+  for (int k = 0; k < K; ++k) v[k] = e * r[k];
+  EKB_UNROLL
+  for (int k = 0; k < K; ++k) t[k] = fma(-v[k], q[k], e);
+  EKB_UNROLL
+  for (int k = 0; k < K; ++k) v[k] = fma(t[k], r[k], v[k]);
+#else
+  for (int k = 0; k < K; ++k) v[k] = e / q[k];
+#endif
+}
+
 // K Sturm counts in one sweep: K independent recurrences interleaved so the divide latency of one hides behind the
 // others (the single-chain kernel was latency-bound: ncu "wait" stalls 3.8 warps/issue, 16 % issue-active).  On the
 // host each count is bit-identical to sturm_count at the same shift.
 template <int K>
 EKB_HD void sturm_count_multi(long long n, const double* __restrict__ d, const double* __restrict__ e2, const double* x,
                               double pivmin, long long* cnt) {
-  double q[K];
+  double q[K], v[K];
   long long c[K];
-EKB_UNROLL
+  EKB_UNROLL
   for (int k = 0; k < K; ++k) {
     q[k] = d[0] - x[k];
     if (fabs(q[k]) < pivmin) q[k] = -pivmin;
@@ -90,15 +120,16 @@ EKB_UNROLL
   }
   for (long long i = 1; i < n; ++i) {
     const double di = d[i], ei = e2[i - 1];
-EKB_UNROLL
+    sturm_quot_multi<K>(ei, q, v);
+    EKB_UNROLL
     for (int k = 0; k < K; ++k) {
-      double t = di - sturm_quot(ei, q[k]) - x[k];
+      double t = di - v[k] - x[k];
       if (fabs(t) < pivmin) t = -pivmin;
       q[k] = t;
       if (t <= 0.0) ++c[k];
     }
   }
-EKB_UNROLL
+  EKB_UNROLL
   for (int k = 0; k < K; ++k) cnt[k] = c[k];
 }
 
