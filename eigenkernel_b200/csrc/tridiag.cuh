@@ -203,33 +203,56 @@ EKB_HD double stein_start(uint64_t j, uint64_t i) {
 EKB_HD void gt_factor(long long n, const double* __restrict__ d, const double* __restrict__ e, double lambda,
                       double* __restrict__ a, double* __restrict__ b, double* __restrict__ c, double* __restrict__ d2,
                       unsigned char* __restrict__ piv) {
-  for (long long i = 0; i < n; ++i) {
-    a[i] = d[i] - lambda;
-    b[i] = i + 1 < n ? e[i] : 0.0;
-    d2[i] = 0.0;
-    c[i] = 0.0;
-    piv[i] = 0;
-  }
-  for (long long i = 0; i + 1 < n; ++i) {
-    const double sub = e[i];  // element (i+1, i)
-    if (fabs(a[i]) >= fabs(sub)) {
-      const double m = a[i] != 0.0 ? sub / a[i] : 0.0;
-      c[i] = m;
-      a[i + 1] -= m * b[i];
+  // The current row (diagonal ai, superdiagonal bi) is carried in registers and the untouched rows are read straight
+  // from d and e, four at a time ahead of the dependent chain: the recurrence never waits on a load of something it
+  // has just stored (the first version read a[i+1] / b[i+1] back from memory every step).
+  constexpr int U = 4;
+  double ai = d[0] - lambda;
+  double bi = n > 1 ? e[0] : 0.0;
+  long long i = 0;
+  auto step = [&](long long row, double sub, double an0, double bn0, bool has_next2) {
+    // sub = e[row] (element (row+1, row)); an0 / bn0 = original diagonal / superdiagonal of row + 1
+    if (fabs(ai) >= fabs(sub)) {
+      const double m = ai != 0.0 ? sub / ai : 0.0;
+      c[row] = m;
+      piv[row] = 0;
+      d2[row] = 0.0;
+      a[row] = ai;
+      b[row] = bi;
+      ai = an0 - m * bi;
+      bi = bn0;
     } else {
-      const double m = a[i] / sub;
-      piv[i] = 1;
-      c[i] = m;
-      const double t = a[i + 1];
-      a[i + 1] = b[i] - m * t;
-      a[i] = sub;
-      b[i] = t;
-      if (i + 2 < n) {
-        d2[i] = b[i + 1];
-        b[i + 1] = -m * d2[i];
-      }
+      const double m = ai / sub;
+      c[row] = m;
+      piv[row] = 1;
+      a[row] = sub;
+      b[row] = an0;
+      const double na = bi - m * an0;
+      d2[row] = has_next2 ? bn0 : 0.0;
+      bi = has_next2 ? -m * bn0 : bn0;
+      ai = na;
     }
+  };
+  for (; i + U + 1 < n; i += U) {  // rows i .. i+U-1, all of which have a row + 2
+    double sub[U], an0[U], bn0[U];
+    EKB_UNROLL
+    for (int u = 0; u < U; ++u) {
+      sub[u] = e[i + u];
+      an0[u] = d[i + u + 1] - lambda;
+      bn0[u] = e[i + u + 1];
+    }
+    EKB_UNROLL
+    for (int u = 0; u < U; ++u) step(i + u, sub[u], an0[u], bn0[u], true);
   }
+  for (; i + 1 < n; ++i) {
+    const bool has2 = i + 2 < n;
+    step(i, e[i], d[i + 1] - lambda, has2 ? e[i + 1] : 0.0, has2);
+  }
+  a[n - 1] = ai;
+  b[n - 1] = 0.0;
+  c[n - 1] = 0.0;
+  d2[n - 1] = 0.0;
+  piv[n - 1] = 0;
 }
 
 // Reciprocal of a pivot of U, with pivots smaller than `pert` replaced by +-pert (dlagts with job = -1).  Applied to
