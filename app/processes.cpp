@@ -54,6 +54,10 @@ void setup_distribution(ek_process_t& proc) {
   proc.my_proc_row = 0;
   proc.my_proc_col = s_rank;
   proc.context = 0;
+  if (proc.my_rank == 0) {  // processes.f90:27-30
+    printf("BLACS process grid: %d x %d (%d)\n", proc.n_procs_row, proc.n_procs_col, proc.n_procs);
+    fflush(stdout);
+  }
 }
 
 // ---------------------------------------------------------------- launcher

@@ -20,8 +20,6 @@ void eigen_solver(ek_argument_t& arg, const ek_sparse_mat_t& matrix_A, ek_eigenp
   if (arg.block_size > 0) g_block_size = arg.block_size;  // do not use the default block size
   setup_distribution(proc);
   if (arg.is_printing_grid_mapping) print_map_of_grid_to_processes(proc);
-  if (check_master() && proc.n_procs > 1)
-    printf("BLACS process grid (b200): %d x %d (%d)\n", proc.n_procs_row, proc.n_procs_col, proc.n_procs);
 
   const std::string& st = arg.solver_type;
   if (st == "b200" || st == "b200_select") {

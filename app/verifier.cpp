@@ -25,8 +25,11 @@ static void check(int info, const char* routine) {
   terminate(std::string(routine) + " failed", info);
 }
 static ekb200_ctx* context() {
-  ek_process_t proc;
-  setup_distribution(proc);
+  ek_process_t proc;  // the grid of the solve: 1 x P in rank order (no second "BLACS process grid" line)
+  proc.my_rank = world_rank();
+  proc.n_procs = world_size();
+  proc.n_procs_col = world_size();
+  proc.my_proc_col = world_rank();
   return b200_context(proc);
 }
 static const int32_t kIjDummy[2] = {1, 1};
