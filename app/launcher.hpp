@@ -16,6 +16,10 @@ struct SharedBoard {
 
 SharedBoard* shared_board();
 void launch_ranks(int nranks);   // after this call world_rank()/world_size() are set in every process
+// Ranks started by an external launcher (mpirun / srun / torchrun --no-python: RANK + WORLD_SIZE, OMPI_COMM_WORLD_*,
+// PMI_*, SLURM_PROCID + SLURM_NTASKS in the environment): attaches this process to a file-backed board under /dev/shm
+// shared by the ranks of the launch.  Returns false when the environment names no multi-rank launch.
+bool attach_external_ranks();
 void world_barrier();
 void finalize_ranks();
 void abort_ranks();

@@ -28,7 +28,12 @@ static int run(int argc, char** argv) {
   for (int i = 1; i + 1 < argc; ++i)
     if (!strcmp(argv[i], "--ngpu")) ngpu = atoi(argv[i + 1]);
   if (ngpu < 1 || ngpu > 8 || (ngpu & (ngpu - 1))) terminate("eigen_test: --ngpu must be 1, 2, 4 or 8", 1);
-  launch_ranks(ngpu);
+  if (ngpu == 1 && attach_external_ranks()) {
+    ngpu = world_size();  // started by mpirun / srun / torchrun --no-python: one rank per B200, like the reference
+    if (ngpu > 8 || (ngpu & (ngpu - 1))) terminate("eigen_test: the B200 solvers run on 1, 2, 4 or 8 ranks", 1);
+  } else {
+    launch_ranks(ngpu);
+  }
 
   world_barrier();
   const double time_start = wtime();

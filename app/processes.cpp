@@ -2,6 +2,7 @@
 // rank-per-GPU launcher of this twin.  `mpirun -np P` does not exist in this image; `--ngpu P` forks P-1 ranks
 // BEFORE the CUDA runtime is touched (fork after CUDA initialisation is undefined), rank r drives GPU r and the
 // 128-byte NCCL id travels through an anonymous shared mapping instead of mpi_bcast.
+#include <fcntl.h>
 #include <signal.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -13,6 +14,8 @@
 #include <unistd.h>
 
 #include <atomic>
+#include <string>
+#include <ctype.h>
 
 #include "ek_app.hpp"
 #include "launcher.hpp"
@@ -113,6 +116,56 @@ void launch_ranks(int nranks) {
   set_world(0, nranks);
 }
 
+// ---------------------------------------------------------------- ranks started by mpirun / srun / torchrun
+static std::string s_board_path;
+
+static bool env_int(const char* name, long* out) {
+  const char* v = getenv(name);
+  if (!v || !*v) return false;
+  char* end = nullptr;
+  long x = strtol(v, &end, 10);
+  if (end == v) return false;
+  *out = x;
+  return true;
+}
+
+bool attach_external_ranks() {
+  static const char* const kRank[] = {"OMPI_COMM_WORLD_RANK", "PMI_RANK", "PMIX_RANK", "SLURM_PROCID", "RANK"};
+  static const char* const kSize[] = {"OMPI_COMM_WORLD_SIZE", "PMI_SIZE", "PMIX_SIZE", "SLURM_NTASKS", "WORLD_SIZE"};
+  long rank = -1, size = -1;
+  for (int i = 0; i < 5 && (rank < 0 || size < 0); ++i) {
+    long r, z;
+    if (env_int(kRank[i], &r) && env_int(kSize[i], &z)) { rank = r; size = z; }
+  }
+  if (size <= 1 || rank < 0 || rank >= size) return false;
+  if (size > 64) terminate("attach_external_ranks: at most 64 ranks", 1);
+  // one board per launch: EKB200_RENDEZVOUS names it, else the launcher's job id, else the launcher's pid (all ranks
+  // of one node are children of the same mpirun / torchrun agent)
+  std::string key;
+  if (const char* v = getenv("EKB200_RENDEZVOUS")) key = v;  // a name, or a path (contains '/')
+  if (key.empty()) {
+    for (const char* name : {"TORCHELASTIC_RUN_ID", "PMIX_NAMESPACE", "OMPI_MCA_ess_base_jobid", "SLURM_STEP_ID", "MASTER_PORT"})
+      if (const char* v = getenv(name)) { key = std::string(name) + "_" + v; break; }
+    key += "_" + std::to_string((long)getppid());
+  }
+  if (key.find('/') == std::string::npos) {
+    for (auto& ch : key)
+      if (!isalnum((unsigned char)ch) && ch != '_' && ch != '-') ch = '_';
+    s_board_path = "/dev/shm/ekb200_" + key;
+  } else {
+    s_board_path = key;
+  }
+  int fd = open(s_board_path.c_str(), O_RDWR | O_CREAT, 0600);
+  if (fd < 0) terminate("attach_external_ranks: cannot open " + s_board_path, 1);
+  if (ftruncate(fd, sizeof(SharedBoard)) != 0) terminate("attach_external_ranks: ftruncate failed", 1);
+  void* m = mmap(nullptr, sizeof(SharedBoard), PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  close(fd);
+  if (m == MAP_FAILED) terminate("attach_external_ranks: mmap failed", 1);
+  s_board = reinterpret_cast<SharedBoard*>(m);  // a fresh file is all zeros: a valid initial board
+  set_world((int)rank, (int)size);
+  return true;
+}
+
 // Sense-reversing barrier over the shared board (mpi_barrier).
 void world_barrier() {
   if (!s_board || s_size <= 1) return;
@@ -128,6 +181,10 @@ void world_barrier() {
 // Rank 0 waits for the others before it leaves (mpi_finalize).
 void finalize_ranks() {
   if (s_size <= 1) return;
+  if (!s_board_path.empty()) {  // external launcher: it reaps the ranks; rank 0 removes the board of this launch
+    if (s_rank == 0) unlink(s_board_path.c_str());
+    return;
+  }
   if (s_rank != 0) return;
   sigset_t block;
   sigemptyset(&block);
@@ -150,6 +207,8 @@ void finalize_ranks() {
 void abort_ranks() {
   if (s_rank == 0)
     for (int i = 0; i < s_num_children; ++i) kill(s_children[i], SIGKILL);
+  // external launcher: it tears the other ranks down when this one exits non-zero; do not leave the board behind
+  if (s_rank == 0 && !s_board_path.empty()) unlink(s_board_path.c_str());
 }
 
 }  // namespace ekapp

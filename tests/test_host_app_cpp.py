@@ -257,6 +257,24 @@ def test_cli_forked_ranks_dry_run(hooks, golden_dir, tmp_path):
     assert r.stdout.count("Eigen Test start") == 1 and "MPI processes: 2" in r.stdout
 
 
+def test_cli_ranks_from_an_external_launcher(hooks, golden_dir, tmp_path):
+    """mpirun / srun / torchrun --no-python export the rank and the world size; the ranks then meet on a file-backed
+    board (EKB200_RENDEZVOUS, by default /dev/shm/ekb200_<job id>_<launcher pid>) instead of being forked."""
+    fa = os.path.join(golden_dir, "ELSES_MATRIX_VCNT400std_A.mtx")
+    board = tmp_path / "board.bin"
+    procs = []
+    for var_r, var_s, r in (("RANK", "WORLD_SIZE", 0), ("OMPI_COMM_WORLD_RANK", "OMPI_COMM_WORLD_SIZE", 1)):
+        env = dict(os.environ, EKB200_RENDEZVOUS=str(board))
+        env[var_r], env[var_s] = str(r), "2"
+        procs.append(subprocess.Popen([APP, "-s", "b200", "--dry-run", fa], cwd=tmp_path, env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.PIPE, text=True))
+    outs = [p.communicate(timeout=60) for p in procs]
+    assert [p.returncode for p in procs] == [0, 0], outs
+    assert outs[0][0].count("Eigen Test start") == 1 and "MPI processes: 2" in outs[0][0]
+    assert outs[1][0].strip() == ""                       # only the master prints (check_master)
+    assert not board.exists()                             # rank 0 removes the board of the launch
+
+
 @pytest.mark.parametrize("args,code,needle", [
     (["-s", "nope", "A"], 1, "[Error] validate_argument: Unknown solver 'nope'"),
     (["-s", "b200", "A", "B"], 1, "[Error] validate_argument: solver 'b200' is not for generalized eigenvalue problem"),
