@@ -22,7 +22,8 @@ ok = True
 
 
 def run(args, cwd):
-    r = subprocess.run([APP, "--ngpu", P] + args, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=150)
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "SLURM_PROCID", "SLURM_NTASKS", "PMI_RANK", "PMI_SIZE")}
+    r = subprocess.run([APP, "--ngpu", P] + args, cwd=cwd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=150)
     if r.returncode != 0:
         print("FAILED rc", r.returncode, r.stdout[-1500:], r.stderr[-1500:])
     return r

@@ -21,9 +21,19 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 APP = os.path.join(ROOT, "app", "bin", "ekb200_app")
 
 
+_LAUNCHER_VARS = ("OMPI_COMM_WORLD_RANK", "OMPI_COMM_WORLD_SIZE", "PMI_RANK", "PMI_SIZE", "PMIX_RANK", "PMIX_SIZE",
+                  "SLURM_PROCID", "SLURM_NTASKS", "RANK", "WORLD_SIZE")
+
+
+def _clean_env():
+    """The app takes its ranks from a launcher's environment when one is set; the tests start single processes."""
+    return {k: v for k, v in os.environ.items() if k not in _LAUNCHER_VARS}
+
+
 def _run(args, cwd, timeout=600):
     assert os.path.exists(APP), "app/bin/ekb200_app is missing: run __graft_entry__.build()"
-    r = subprocess.run([APP] + args, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout)
+    r = subprocess.run([APP] + args, cwd=cwd, env=_clean_env(), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                       timeout=timeout)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     return r
 

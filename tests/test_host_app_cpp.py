@@ -230,8 +230,18 @@ def test_parser_fuzz_against_python_reader(hooks, tmp_path):
         assert dims == (n, n, nnz) and np.array_equal(ij, ref.suffix) and np.array_equal(v, ref.value)
 
 
+_LAUNCHER_VARS = ("OMPI_COMM_WORLD_RANK", "OMPI_COMM_WORLD_SIZE", "PMI_RANK", "PMI_SIZE", "PMIX_RANK", "PMIX_SIZE",
+                  "SLURM_PROCID", "SLURM_NTASKS", "RANK", "WORLD_SIZE")
+
+
+def _clean_env():
+    """The app takes its ranks from a launcher's environment when one is set; the tests start single processes."""
+    return {k: v for k, v in os.environ.items() if k not in _LAUNCHER_VARS}
+
+
 def _run(args, cwd):
-    return subprocess.run([APP] + args, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
+    return subprocess.run([APP] + args, cwd=cwd, env=_clean_env(), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                          timeout=120)
 
 
 def test_cli_dry_run_prints_the_reference_configuration_block(hooks, golden_dir, tmp_path):
@@ -264,7 +274,7 @@ def test_cli_ranks_from_an_external_launcher(hooks, golden_dir, tmp_path):
     board = tmp_path / "board.bin"
     procs = []
     for var_r, var_s, r in (("RANK", "WORLD_SIZE", 0), ("OMPI_COMM_WORLD_RANK", "OMPI_COMM_WORLD_SIZE", 1)):
-        env = dict(os.environ, EKB200_RENDEZVOUS=str(board))
+        env = dict(_clean_env(), EKB200_RENDEZVOUS=str(board))
         env[var_r], env[var_s] = str(r), "2"
         procs.append(subprocess.Popen([APP, "-s", "b200", "--dry-run", fa], cwd=tmp_path, env=env, stdout=subprocess.PIPE,
                                       stderr=subprocess.PIPE, text=True))
