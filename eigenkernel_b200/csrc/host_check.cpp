@@ -6,6 +6,8 @@
 #include "tridiag.cuh"
 #include <algorithm>
 #include <cmath>
+#include <atomic>
+#include <thread>
 #include <vector>
 
 extern "C" int ekb200_host_secular(int k, const double* d, const double* z, double rho, double* lam, int* orig,
@@ -122,5 +124,84 @@ extern "C" int ekb200_host_stein(long long n, const double* d, const double* e, 
   }
   if (nclusters) *nclusters = nc;
   if (max_cluster) *max_cluster = mc;
+  return fail;
+}
+
+// ---- the per-cluster procedure run the way a warp runs it: W host threads in lock step stand in for the lanes
+// (lane 0 runs the serial recurrences, all lanes the strided vector work), with the butterfly reduction order of the
+// __shfl_xor_sync sums.  Checks the SPMD orchestration of stein_cluster (sync placement, lane-0-only sections,
+// strided loops) on the CPU.
+namespace {
+struct SpinBarrier {
+  std::atomic<int> count{0}, gen{0};
+  int n;
+  explicit SpinBarrier(int n_) : n(n_) {}
+  void wait() {
+    const int g = gen.load();
+    if (count.fetch_add(1) + 1 == n) {
+      count.store(0);
+      gen.fetch_add(1);
+    } else {
+      while (gen.load() == g) std::this_thread::yield();
+    }
+  }
+};
+struct LaneTeam {
+  int lane_, width_;
+  SpinBarrier* bar;
+  double* slots;
+  int lane() const { return lane_; }
+  int width() const { return width_; }
+  void sync() const { bar->wait(); }
+  double sum(double v) const {
+    for (int o = width_ / 2; o > 0; o >>= 1) {
+      slots[lane_] = v;
+      bar->wait();
+      v += slots[lane_ ^ o];
+      bar->wait();
+    }
+    return v;
+  }
+  double max(double v) const {
+    for (int o = width_ / 2; o > 0; o >>= 1) {
+      slots[lane_] = v;
+      bar->wait();
+      v = std::fmax(v, slots[lane_ ^ o]);
+      bar->wait();
+    }
+    return v;
+  }
+  double bcast0(double v) const {
+    if (lane_ == 0) slots[0] = v;
+    bar->wait();
+    const double r = slots[0];
+    bar->wait();
+    return r;
+  }
+};
+}  // namespace
+
+extern "C" int ekb200_host_stein_lanes(long long n, const double* d, const double* e, long long nev, const double* w,
+                                       int lanes, double* Z, long long ldz) {
+  std::vector<double> e2;
+  double gl, gu, onenrm, pivmin;
+  tri_setup(n, d, e, e2, &gl, &gu, &onenrm, &pivmin);
+  const double ortol = ekb::stein_ortol(nev, w, onenrm);
+  std::vector<long long> starts((size_t)nev + 2);
+  const long long nc = ekb::stein_clusters(0, nev, w, ortol, starts.data());
+  std::vector<double> ws((size_t)(4 * n + (n + 7) / 8 + 8));
+  std::vector<double> slots((size_t)lanes);
+  std::vector<int> fails((size_t)nc + 1, 0);
+  SpinBarrier bar(lanes);
+  std::vector<std::thread> th;
+  for (int l = 0; l < lanes; ++l)
+    th.emplace_back([&, l]() {
+      LaneTeam tm{l, lanes, &bar, slots.data()};
+      for (long long c = 0; c < nc; ++c)
+        ekb::stein_cluster(tm, n, d, e, w, starts[c], starts[c + 1], Z, ldz, 0, ws.data(), onenrm, &fails[c]);
+    });
+  for (auto& t : th) t.join();
+  int fail = 0;
+  for (int f : fails) fail += f;
   return fail;
 }

@@ -28,6 +28,7 @@ def hc():
     lib = ctypes.CDLL(HC)
     lib.ekb200_host_stebz.argtypes = [ll, dp, dp, dp, ctypes.POINTER(ctypes.c_int)]
     lib.ekb200_host_stebz_k.argtypes = [ll, dp, dp, ctypes.c_int, dp, ctypes.POINTER(ctypes.c_int)]
+    lib.ekb200_host_stein_lanes.argtypes = [ll, dp, dp, ll, dp, ctypes.c_int, dp, ll]
     lib.ekb200_host_stein_slab.argtypes = [ll, dp, dp, ll, dp, ll, ll, dp, ll]
     lib.ekb200_host_stein.argtypes = [ll, dp, dp, ll, dp, dp, ll, ctypes.POINTER(ll), ctypes.POINTER(ll)]
     return lib
@@ -211,3 +212,20 @@ def test_slabs_of_a_sharded_solve_reproduce_the_single_rank_vectors(hc):
             Zs[:, lo:hi] = Zr[:, lo:hi]
         assert np.array_equal(Zs, Z1)
     check(d, e, w, Z1)
+
+
+@pytest.mark.parametrize("name", ["random", "glued_exact_double", "glued_tiny_coupling", "wilkinson21", "n2", "diagonal"])
+def test_warp_style_execution_of_the_cluster_procedure(hc, name):
+    """stein_cluster executed the way the CUDA kernel executes it: 32 (here also 8) lanes in lock step, lane 0 on the
+    serial recurrences, all lanes on the strided vector work, butterfly reductions -- same quality as the 1-lane run."""
+    d, e = cases()[name]
+    n = len(d)
+    nev = min(n, 120)
+    w, _ = stebz(hc, d, e)
+    ee = np.ascontiguousarray(e if n > 1 else np.zeros(1))
+    for lanes in (32, 8):
+        Z = np.zeros((n, nev), order="F")
+        fail = hc.ekb200_host_stein_lanes(n, d.ctypes.data_as(dp), ee.ctypes.data_as(dp), nev, w.ctypes.data_as(dp), lanes,
+                                          Z.ctypes.data_as(dp), n)
+        assert fail == 0
+        check(d, e, w, Z)
