@@ -88,6 +88,21 @@ def cpu_threads() -> int:
     return lt.get_num_threads()
 
 
+def cpu_rate_table(sizes, cores: int) -> dict:
+    """The oracle port timed once at each n of `sizes` (rates at >= 3 sizes so the trend towards the
+    metric's n = 32768 is visible) + a cubic extrapolation of the seconds at n = 32768 from the largest sample,
+    LABELLED as extrapolated (the rate still rises slowly with n, so this is an upper bound on the CPU seconds)."""
+    rows = []
+    for m in sizes:
+        dt, tm = cpu_solve_once(m)
+        rows.append({"n": m, "seconds": dt, "tflops": canonical_flops(m) / dt / 1e12, "stage_seconds": tm})
+    big = rows[-1]
+    return {"cores": cores, "sizes": rows,
+            "extrapolated_seconds_n32768": big["seconds"] * (32768.0 / big["n"]) ** 3,
+            "extrapolation": f"EXTRAPOLATED, not measured: seconds at n={big['n']} x (32768/{big['n']})^3, i.e. the "
+                             f"rate measured at n={big['n']} held constant"}
+
+
 def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -104,6 +119,13 @@ def run_reference(args) -> None:
         stages = tm
     sec = sum(t) / len(t)
     val = canonical_flops(n) / sec / 1e12
+    table = None
+    if not args.no_cpu_table:  # once, outside the K timed steps
+        table = cpu_rate_table([x for x in args.cpu_sizes if x != n], cores)
+        table["sizes"].append({"n": n, "seconds": sec, "tflops": val, "stage_seconds": stages})
+        table["sizes"].sort(key=lambda r: r["n"])
+        big = table["sizes"][-1]
+        table["extrapolated_seconds_n32768"] = big["seconds"] * (32768.0 / big["n"]) ** 3
     sample = (f"oracle port (serial-LAPACK twins dpotrf/dsygst/dsytrd/dstedc/dormtr/dtrtrs, OpenBLAS, {cores} threads) "
               f"on n={n} of the same generator; canonical 7n^3 FLOPs; the Fortran/MPI/ScaLAPACK reference cannot be "
               f"built in this image")
@@ -113,7 +135,7 @@ def run_reference(args) -> None:
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args.n), "sample_n": n},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-                         "stage_seconds": stages},
+                         "stage_seconds": stages, "rate_table": table},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
@@ -181,6 +203,60 @@ def mem_available_bytes():
     except OSError:
         pass
     return None
+
+
+# ------------------------------------------------------------------------------------------ acceptance
+def acceptance(ctx, n, ld, dA, dB, dZ, dw, fill, world, rank, local, dist, w_last) -> dict:
+    """BASELINE.json's acceptance numbers for the LAST timed solve, computed on the device by the library's twins of
+    the reference's own checks (verifier.f90:140-199 residual, :279-325 orthogonality; called as main.f90:149-179
+    calls them): max_j ||A x_j - lambda_j B x_j||_2 / ||A||_F, the scaled-Gram metric, and || X^T B X - I ||_F.
+    With P > 1 ranks the eigenvalues are also compared with a single-GPU solve of the same problem (a second,
+    communicator-less context on rank 0)."""
+    import numpy as np
+    from ctypes import byref, c_double
+
+    fill()  # the solve destroyed A and left L in B: regenerate both from the counter hash
+    if world > 1:
+        ctx.call("ekb200_comm_allgather_slabs", n, n, dZ, ld)  # the Gram matrix needs every column on every rank
+    an, ave, mx, o, g = c_double(), c_double(), c_double(), c_double(), c_double()
+    ctx.call("ekb200_eval_residual_norm_dev", n, n, dA, ld, dB, ld, dw, dZ, ld, byref(an), byref(ave), byref(mx))
+    ctx.call("ekb200_eval_b_orthonormality_dev", n, 1, n, dZ, ld, dB, ld, byref(o), byref(g))
+    tol = 1e-12 * n
+    out = {"n": n, "checked_vectors": n, "A_norm_fro": an.value,
+           "residual_max_over_A": mx.value, "residual_ave_over_A": ave.value,
+           "orthogonality_verifier": o.value, "xtbx_minus_identity_fro": g.value, "tolerance": tol,
+           "definitions": "residual = max_j ||A x_j - lambda_j B x_j||_2 / ||A||_F (verifier.f90:179-199, no division "
+                          "by ||x_j||; ||x_j||_2 ~ 0.7 here since B ~ 2 I); orthogonality_verifier = Frobenius norm of "
+                          "the unit-diagonal-scaled Gram matrix X^T B X with its diagonal zeroed (verifier.f90:310-325)"}
+    dl = None
+    if world > 1:
+        ctx.set_option("cache_device_memory", 0)  # hand the arena's cached blocks back before the solo solve
+        ctx.set_option("cache_device_memory", 1)
+        if rank == 0:
+            from eigenkernel_b200.device import Context
+
+            solo = Context(local)
+            a, b, z = solo.alloc(ld * n * 8), solo.alloc(ld * n * 8), solo.alloc(ld * n * 8)
+            w1d = solo.alloc((n + 8) * 8)
+            solo.call("ekb200_fill_synthetic", n, SEED, 1.0, 0, 0.0, a, ld)
+            solo.call("ekb200_fill_synthetic", n, SEED + 1, float(n), 1, 2.0, b, ld)
+            info = solo.call("ekb200_sygvd_dev", n, n, a, ld, b, ld, w1d, z, ld)
+            assert info == 0, info
+            w1 = np.zeros(n)
+            solo.call("ekb200_d2h", w1.ctypes.data, w1d, n * 8)
+            solo.close()
+            scale = float(np.abs(w1).max())
+            dl = {"max_abs_over_max_lambda": float(np.abs(w_last - w1).max() / scale),
+                  "max_relative": float((np.abs(w_last - w1) / np.maximum(np.abs(w1), 1e-300)).max()),
+                  "smallest_abs_lambda": float(np.abs(w1).min()), "tolerance": 1e-10,
+                  "note": "max_relative is ill-conditioned for |lambda| << ||A|| (SURVEY 8(d)); the test is on "
+                          "max|dlambda| / max|lambda|"}
+    out["dlambda_vs_1gpu"] = dl if world > 1 else None
+    ok = mx.value <= tol and g.value <= tol and o.value <= tol
+    if dl is not None:
+        ok = ok and dl["max_abs_over_max_lambda"] <= 1e-10
+    out["pass"] = bool(ok)
+    return out
 
 
 # ------------------------------------------------------------------------------------------ our arm
@@ -280,6 +356,10 @@ def run_ours(args) -> None:
     wv = np.zeros(n)
     ctx.call("ekb200_d2h", wv.ctypes.data, dw, n * 8)
     assert np.all(np.isfinite(wv)) and np.all(np.diff(wv) >= 0), "eigenvalues not ascending/finite"
+    acc = None
+    if not args.no_check:
+        acc = acceptance(ctx, n, ld, dA, dB, dZ, dw, fill, world, rank, local, dist, wv)
+        barrier()
 
     # ---- e2e: host buffers through the reference-facing entry point
     e2e = None
@@ -368,7 +448,16 @@ def run_ours(args) -> None:
     if not args.no_cpu:
         cores = cpu_threads()
         dt, tm = cpu_solve_once(args.cpu_n)
+        table = None
+        if not args.no_cpu_table:
+            table = cpu_rate_table([x for x in args.cpu_sizes if x != args.cpu_n], cores)
+            table["sizes"].append({"n": args.cpu_n, "seconds": dt, "tflops": canonical_flops(args.cpu_n) / dt / 1e12,
+                                   "stage_seconds": tm})
+            table["sizes"].sort(key=lambda r: r["n"])
+            big = table["sizes"][-1]
+            table["extrapolated_seconds_n32768"] = big["seconds"] * (32768.0 / big["n"]) ** 3
         cpu = {"value": canonical_flops(args.cpu_n) / dt / 1e12, "unit": UNIT, "cores": cores, "kind": "port",
+               "rate_table": table,
                "sample": f"oracle port (serial-LAPACK twins of the reference's call sequence, OpenBLAS, {cores} "
                          f"threads) on n={args.cpu_n} of the same generator, {dt:.1f} s; the reference itself "
                          f"(Fortran+MPI+ScaLAPACK) cannot be built in this image",
@@ -386,9 +475,11 @@ def run_ours(args) -> None:
         "seconds_per_solve": seconds / K, "wall_seconds_per_solve": wall / K,
         "clocks": clocks, "e2e": e2e if e2e is not None else ({"skipped": e2e_skip} if e2e_skip else None),
         "gpu_launches": int(launches), "nccl_collectives": int(collectives), "roofline": roof, "stages": stages,
-        "kernel_profile": prof_rows, "fp64_peak_measured": peak, "cpu_baseline": cpu,
+        "kernel_profile": prof_rows, "fp64_peak_measured": peak, "cpu_baseline": cpu, "acceptance": acc,
     }
     emit(line)
+    if acc is not None and not acc["pass"]:
+        raise AssertionError(f"acceptance check failed: {acc}")
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()
@@ -404,6 +495,11 @@ def main():
     ap.add_argument("--cpu-n", type=int, default=6144, dest="cpu_n")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-check", action="store_true", dest="no_check",
+                    help="skip the residual / orthogonality / eigenvalue acceptance check of the last timed solve")
+    ap.add_argument("--cpu-sizes", type=lambda t: [int(x) for x in t.split(",")], default=[4096, 6144, 8192],
+                    dest="cpu_sizes", help="orders n at which the CPU oracle port is also timed once (rate table)")
+    ap.add_argument("--no-cpu-table", action="store_true", dest="no_cpu_table")
     args = ap.parse_args()
     quiet_stdout()
     if args.impl == "reference":

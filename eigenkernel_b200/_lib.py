@@ -87,6 +87,8 @@ _SIGS = {
                                       c_void_p, c_int64, POINTER(c_double), POINTER(c_double), POINTER(c_double)],
     "ekb200_eval_orthogonality_dev": [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64,
                                       POINTER(c_double)],
+    "ekb200_eval_b_orthonormality_dev": [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64,
+                                         POINTER(c_double), POINTER(c_double)],
     "ekb200_get_ipratios_dev": [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p],
     "ekb200_comm_unique_id": [c_void_p],
     "ekb200_comm_init": [c_void_p, c_int, c_int, c_void_p],

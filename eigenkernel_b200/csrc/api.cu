@@ -639,6 +639,18 @@ int ekb200_eval_orthogonality_dev(ekb200_ctx* h, int64_t n, int64_t index1, int6
   if (B && ldb < n) return -8;
   return eval_orthogonality(ctx, n, index1, index2, X, ldx, B, ldb, orthogonality);
 }
+int ekb200_eval_b_orthonormality_dev(ekb200_ctx* h, int64_t n, int64_t index1, int64_t index2, const double* X,
+                                     int64_t ldx, const double* B, int64_t ldb, double* orthogonality,
+                                     double* gram_minus_identity) {
+  CHECK_CTX(h);
+  if (n <= 0) return -2;
+  if (index1 < 1) return -3;
+  if (index2 < index1 || index2 > n) return -4;
+  if (!X) return -5;
+  if (ldx < n) return -6;
+  if (B && ldb < n) return -8;
+  return eval_orthogonality(ctx, n, index1, index2, X, ldx, B, ldb, orthogonality, gram_minus_identity);
+}
 int ekb200_get_ipratios_dev(ekb200_ctx* h, int64_t n, int64_t nvec, const double* X, int64_t ldx, const double* B,
                             int64_t ldb, double* ipratios) {
   CHECK_CTX(h);

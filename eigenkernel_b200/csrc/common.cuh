@@ -201,7 +201,7 @@ int sygst_dist(Ctx* ctx, i64 n, double* A, i64 lda, const double* L, i64 ldl, co
 int eval_residual_norm(Ctx* ctx, i64 n, i64 ncheck, const double* A, i64 lda, const double* B, i64 ldb, const double* w,
                        const double* Xfull, i64 ldx, double* A_norm, double* res_ave, double* res_max);
 int eval_orthogonality(Ctx* ctx, i64 n, i64 index1, i64 index2, const double* Xfull, i64 ldx, const double* B, i64 ldb,
-                       double* orthogonality);
+                       double* orthogonality, double* gram_minus_identity = nullptr);
 int get_ipratios(Ctx* ctx, i64 n, i64 nvec, const double* Xfull, i64 ldx, const double* B, i64 ldb, double* ipr);
 
 }  // namespace ekb

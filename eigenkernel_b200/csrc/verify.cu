@@ -91,27 +91,38 @@ __global__ void gram_diag_kernel(const double* __restrict__ G, i64 ldg, i64 row0
   if (j < kc) dg[j] = G[j * ldg + row0 + j];
 }
 
-// partial sums of (G_ij / sqrt(d_i d_j))^2 over the off-diagonal elements of the slab (verifier.f90:310-325)
+// partial sums over the slab of (a) (G_ij / sqrt(d_i d_j))^2 for the off-diagonal elements (verifier.f90:310-325) and
+// (b) (G_ij - delta_ij)^2 for ALL elements (|| X^T B X - I ||_F^2, the north-star metric: it also tests normalisation)
 __global__ void __launch_bounds__(256) gram_offdiag_kernel(const double* __restrict__ G, i64 ldg, i64 k, i64 row0, i64 kc,
-                                                           const double* __restrict__ dall, double* __restrict__ out) {
-  __shared__ double red[8];
-  double s = 0.0;
+                                                           const double* __restrict__ dall, double* __restrict__ out,
+                                                           double* __restrict__ out2) {
+  __shared__ double red[8], red2[8];
+  double s = 0.0, s2 = 0.0;
   for (i64 j = blockIdx.y; j < kc; j += gridDim.y) {
     const double dj = dall[row0 + j];
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < k; i += (i64)gridDim.x * blockDim.x) {
-      if (i == row0 + j) continue;
-      const double x = G[j * ldg + i] * (1.0 / sqrt(dall[i])) * (1.0 / sqrt(dj));
+      const double g = G[j * ldg + i];
+      if (i == row0 + j) {
+        s2 += (g - 1.0) * (g - 1.0);
+        continue;
+      }
+      s2 += g * g;
+      const double x = g * (1.0 / sqrt(dall[i])) * (1.0 / sqrt(dj));
       s += x * x;
     }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = s; red2[threadIdx.x >> 5] = s2; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    double t = 0.0;
-    for (int q = 0; q < 8; ++q) t += red[q];
+    double t = 0.0, t2 = 0.0;
+    for (int q = 0; q < 8; ++q) { t += red[q]; t2 += red2[q]; }
     out[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = t;
+    out2[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = t2;
   }
 }
 
@@ -207,7 +218,7 @@ int eval_residual_norm(Ctx* ctx, i64 n, i64 ncheck, const double* A, i64 lda, co
 
 // Xfull: n x (>= index2) eigenvectors, ALL columns index1..index2 (1-based, inclusive) valid on every rank.
 int eval_orthogonality(Ctx* ctx, i64 n, i64 index1, i64 index2, const double* Xfull, i64 ldx, const double* B, i64 ldb,
-                       double* orthogonality) {
+                       double* orthogonality, double* gram_minus_identity) {
   StageTimer total(ctx, "eval_orthogonality_b200");
   const i64 k = index2 - index1 + 1;
   const double* V = Xfull + (index1 - 1) * ldx;
@@ -220,7 +231,7 @@ int eval_orthogonality(Ctx* ctx, i64 n, i64 index1, i64 index2, const double* Xf
   if (B) EKB_TRY(tmp.get(&BV, (size_t)ldn * (kc > 0 ? kc : 1)));
   EKB_TRY(tmp.get(&G, (size_t)ldk * (kc > 0 ? kc : 1)));
   EKB_TRY(tmp.get(&dall, (size_t)k + 8));
-  EKB_TRY(tmp.get(&partial, PGX * PGY));
+  EKB_TRY(tmp.get(&partial, 2 * PGX * PGY));
   EKB_TRY(tmp.get(&scal, 8));
   EKB_CUDA(cudaMemsetAsync(dall, 0, ((size_t)k + 8) * sizeof(double), ctx->stream));
   EKB_CUDA(cudaMemsetAsync(scal, 0, 8 * sizeof(double), ctx->stream));
@@ -243,14 +254,17 @@ int eval_orthogonality(Ctx* ctx, i64 n, i64 index1, i64 index2, const double* Xf
   }
   EKB_TRY(comm_allreduce_sum(ctx, dall, (size_t)k));
   if (kc > 0) {
-    gram_offdiag_kernel<<<dim3(PGX, PGY), 256, 0, ctx->stream>>>(G, ldk, k, c0, kc, dall, partial); EKB_COUNT_LAUNCH(ctx);
+    gram_offdiag_kernel<<<dim3(PGX, PGY), 256, 0, ctx->stream>>>(G, ldk, k, c0, kc, dall, partial, partial + PGX * PGY);
+    EKB_COUNT_LAUNCH(ctx);
     sum_final_kernel<<<1, 256, 0, ctx->stream>>>(partial, PGX * PGY, scal); EKB_COUNT_LAUNCH(ctx);
+    sum_final_kernel<<<1, 256, 0, ctx->stream>>>(partial + PGX * PGY, PGX * PGY, scal + 1); EKB_COUNT_LAUNCH(ctx);
     EKB_CUDA(cudaGetLastError());
   }
-  EKB_TRY(comm_allreduce_sum(ctx, scal, 1));
-  double s2 = 0.0;
-  EKB_TRY(d2h_sync(ctx, &s2, scal, sizeof(double)));
-  if (orthogonality) *orthogonality = sqrt(s2);
+  EKB_TRY(comm_allreduce_sum(ctx, scal, 2));
+  double s2[2] = {0.0, 0.0};
+  EKB_TRY(d2h_sync(ctx, s2, scal, 2 * sizeof(double)));
+  if (orthogonality) *orthogonality = sqrt(s2[0]);
+  if (gram_minus_identity) *gram_minus_identity = sqrt(s2[1]);
   total.stop();
   return 0;
 }

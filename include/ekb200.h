@@ -198,6 +198,12 @@ int ekb200_eval_residual_norm_dev(ekb200_ctx* ctx, int64_t n, int64_t ncheck, co
                                   double* A_norm, double* res_norm_ave, double* res_norm_max);
 int ekb200_eval_orthogonality_dev(ekb200_ctx* ctx, int64_t n, int64_t index1, int64_t index2, const double* dev_X,
                                   int64_t ldx, const double* dev_B, int64_t ldb, double* orthogonality);
+/* ekb200_eval_b_orthonormality_dev: the same Gram matrix, two numbers: `orthogonality` as above (verifier.f90:310-325)
+ * and `gram_minus_identity` = || X^T B X - I ||_F including the diagonal, i.e. BASELINE.json's B-orthogonality
+ * acceptance metric (the reference's own metric does not test normalisation).  Either output may be NULL. */
+int ekb200_eval_b_orthonormality_dev(ekb200_ctx* ctx, int64_t n, int64_t index1, int64_t index2, const double* dev_X,
+                                     int64_t ldx, const double* dev_B, int64_t ldb, double* orthogonality,
+                                     double* gram_minus_identity);
 int ekb200_get_ipratios_dev(ekb200_ctx* ctx, int64_t n, int64_t nvec, const double* dev_X, int64_t ldx,
                             const double* dev_B, int64_t ldb, double* ipratios);
 

@@ -60,13 +60,21 @@ for n in sizes:
         for m in (dd, de, dw, dZ):
             m.free()
     elif what == "select":
-        k = max(n // 10, 1)
-        for method in (1, 2):
+        k = int(os.environ.get("EKB_SELECT_K", max(n // 10, 1)))
+        methods = [int(x) for x in os.environ.get("EKB_SELECT_METHODS", "1,2").split(",")]
+        for method in methods:
             ctx.set_option("select_method", method)
             dA, dw, dZ = ctx.matrix(n, n), ctx.matrix(n, 1), ctx.matrix(n, k)
             ctx.call("ekb200_fill_synthetic", n, 20240603, 1.0, 0, 0.0, dA.ptr, dA.ld)
             ctx.clear_events()
-            info, sec = timed(lambda: ctx.call("ekb200_syevd_dev", n, k, dA.ptr, dA.ld, dw.ptr, dZ.ptr, dZ.ld))
+            try:
+                info, sec = timed(lambda: ctx.call("ekb200_syevd_dev", n, k, dA.ptr, dA.ld, dw.ptr, dZ.ptr, dZ.ld))
+            except Exception as exc:  # e.g. the D&C workspaces do not fit at n = 65536: record and go on
+                out.append({"what": what, "n": n, "k": k, "select_method": method, "error": str(exc)})
+                print(json.dumps(out[-1]), flush=True)
+                for m in (dA, dw, dZ):
+                    m.free()
+                continue
             ev = {name: s for name, s, _ in ctx.events()}
             # check on the device: residual and orthogonality of the k pairs
             ctx.call("ekb200_fill_synthetic", n, 20240603, 1.0, 0, 0.0, dA.ptr, dA.ld)

@@ -183,3 +183,27 @@ def test_clustered_and_degenerate_spectra(ctx):
     r = lt.residual_metrics(A, w, X)
     o = lt.orthogonality_metrics(X)
     assert r["res_max_over_A"] <= 1e-12 * n and o["orth_fro"] <= 1e-12 * n
+
+
+def test_config3_generalized_n8192_matches_oracle(ctx):
+    """BASELINE.json config 3: synthetic generalized n = 8192 (seed 20240601), all eigenpairs, one B200, against the
+    oracle's eigenvalues (the serial-LAPACK twin of general_scalapack; ~15 s of host time) and the three acceptance
+    bars, computed twice: on the host from the downloaded eigenvectors and on the device by the verifier twins."""
+    import ctypes
+
+    n, seed = 8192, 20240601
+    A, B = lt.synthetic_pair(n, seed)
+    w_ref = lt.general_scalapack_twin(A, B)[0]
+    w, X = np.zeros(n), np.zeros((n, n), order="F")
+    assert ctx.call("ekb200_sygvd", n, n, A.ctypes.data, n, B.ctypes.data, n, w.ctypes.data, X.ctypes.data, n) == 0
+    check_pairs(A, B, w, X, w_ref)
+    dA, dB, dX, dw = ctx.from_numpy(A), ctx.from_numpy(B), ctx.from_numpy(X), ctx.from_numpy(w)
+    an, ave, mx, o, g = (ctypes.c_double() for _ in range(5))
+    ctx.call("ekb200_eval_residual_norm_dev", n, n, dA.ptr, dA.ld, dB.ptr, dB.ld, dw.ptr, dX.ptr, dX.ld,
+             ctypes.byref(an), ctypes.byref(ave), ctypes.byref(mx))
+    ctx.call("ekb200_eval_b_orthonormality_dev", n, 1, n, dX.ptr, dX.ld, dB.ptr, dB.ld, ctypes.byref(o), ctypes.byref(g))
+    print(f"config3 n={n}: residual_max/||A||={mx.value:.3e} ||X^T B X - I||_F={g.value:.3e} "
+          f"max|dlambda|/max|lambda|={np.abs(w - w_ref).max() / np.abs(w_ref).max():.3e}")
+    assert mx.value <= 1e-12 * n and g.value <= 1e-12 * n and o.value <= 1e-12 * n
+    for m in (dA, dB, dX, dw):
+        m.free()

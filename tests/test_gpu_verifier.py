@@ -73,3 +73,24 @@ def test_argument_errors_mirror_reference(ctx):
     ep.blacs.desc[5] = 32
     with pytest.raises(app_io.TerminateError):
         verifier.eval_orthogonality_blacs(1, 10, ep, _coo(B), ctx=ctx)
+
+
+@pytest.mark.parametrize("n,generalized", [(257, True), (500, False)])
+def test_b_orthonormality_dev_matches_oracle(ctx, n, generalized):
+    """|| X^T B X - I ||_F (BASELINE.json's B-orthogonality metric; bench.py's acceptance block) next to the
+    reference's scaled-Gram number, both from one device pass, against the oracle's restatement."""
+    import ctypes
+
+    A, B = lt.synthetic_pair(n, 300 + n)
+    X = lt.general_scalapack_twin(A, B)[1] if generalized else lt.scalapack_twin(A)[1]
+    X = np.asfortranarray(X * (1.0 + 1e-9 * np.arange(n))[None, :] + 1e-10 * np.random.default_rng(n).standard_normal(X.shape))
+    dX, dB = ctx.from_numpy(X), ctx.from_numpy(B)
+    o, g = ctypes.c_double(), ctypes.c_double()
+    i1, i2 = 3, n - 5
+    ctx.call("ekb200_eval_b_orthonormality_dev", n, i1, i2, dX.ptr, dX.ld, dB.ptr if generalized else None, dB.ld,
+             ctypes.byref(o), ctypes.byref(g))
+    ref = lt.orthogonality_metrics(X[:, i1 - 1:i2], B if generalized else None)
+    assert abs(o.value - ref["verifier_orthogonality"]) <= 1e-6 * ref["verifier_orthogonality"]
+    assert abs(g.value - ref["orth_fro"]) <= 1e-6 * ref["orth_fro"]
+    dX.free()
+    dB.free()
