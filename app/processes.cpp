@@ -8,7 +8,9 @@
 #include <stdlib.h>
 #include <string.h>
 #include <sys/mman.h>
+#include <errno.h>
 #include <sys/prctl.h>
+#include <sys/stat.h>
 #include <sys/wait.h>
 #include <time.h>
 #include <unistd.h>
@@ -129,20 +131,52 @@ static bool env_int(const char* name, long* out) {
   return true;
 }
 
+static constexpr unsigned kBoardMagic = 0x454b4232u;  // "EKB2"
+
+static double rendezvous_timeout() {
+  long t = 120;
+  env_int("EKB200_RENDEZVOUS_TIMEOUT", &t);
+  return t > 0 ? (double)t : 120.0;
+}
+
+[[noreturn]] static void rendezvous_failed(const std::string& what) {
+  if (s_rank == 0 && !s_board_path.empty()) unlink(s_board_path.c_str());
+  terminate("rendezvous of " + std::to_string(s_size) + " ranks timed out (" + what + "): rank " + std::to_string(s_rank) +
+                " waited " + std::to_string((long)rendezvous_timeout()) + " s on " + s_board_path +
+                " -- were all ranks started on this node (mpirun / srun / torchrun)?  EKB200_RENDEZVOUS_TIMEOUT sets the deadline",
+            1);
+}
+
 bool attach_external_ranks() {
+  // opt-in (an sbatch script running the binary once still has SLURM_PROCID / SLURM_NTASKS in its environment)
+  const char* optin = getenv("EKB200_EXTERNAL_RANKS");
+  const char* named = getenv("EKB200_RENDEZVOUS");
+  if (!((optin && atoi(optin) == 1) || (named && *named))) return false;
   static const char* const kRank[] = {"OMPI_COMM_WORLD_RANK", "PMI_RANK", "PMIX_RANK", "SLURM_PROCID", "RANK"};
   static const char* const kSize[] = {"OMPI_COMM_WORLD_SIZE", "PMI_SIZE", "PMIX_SIZE", "SLURM_NTASKS", "WORLD_SIZE"};
-  long rank = -1, size = -1;
+  static const char* const kLocal[] = {"OMPI_COMM_WORLD_LOCAL_SIZE", "MPI_LOCALNRANKS", "", "SLURM_NTASKS_PER_NODE",
+                                       "LOCAL_WORLD_SIZE"};
+  long rank = -1, size = -1, local = -1;
   for (int i = 0; i < 5 && (rank < 0 || size < 0); ++i) {
     long r, z;
-    if (env_int(kRank[i], &r) && env_int(kSize[i], &z)) { rank = r; size = z; }
+    if (env_int(kRank[i], &r) && env_int(kSize[i], &z)) {
+      rank = r;
+      size = z;
+      long l;
+      if (*kLocal[i] && env_int(kLocal[i], &l)) local = l;
+    }
   }
   if (size <= 1 || rank < 0 || rank >= size) return false;
   if (size > 64) terminate("attach_external_ranks: at most 64 ranks", 1);
+  // the board lives in this node's /dev/shm and the B200 solvers use the GPUs of ONE box
+  if (local > 0 && local != size)
+    terminate("attach_external_ranks: " + std::to_string(size) + " ranks but only " + std::to_string(local) +
+                  " on this node: the B200 solvers run on the GPUs of one node",
+              1);
   // one board per launch: EKB200_RENDEZVOUS names it, else the launcher's job id, else the launcher's pid (all ranks
   // of one node are children of the same mpirun / torchrun agent)
   std::string key;
-  if (const char* v = getenv("EKB200_RENDEZVOUS")) key = v;  // a name, or a path (contains '/')
+  if (named) key = named;  // a name, or a path (contains '/')
   if (key.empty()) {
     for (const char* name : {"TORCHELASTIC_RUN_ID", "PMIX_NAMESPACE", "OMPI_MCA_ess_base_jobid", "SLURM_STEP_ID", "MASTER_PORT"})
       if (const char* v = getenv(name)) { key = std::string(name) + "_" + v; break; }
@@ -155,26 +189,78 @@ bool attach_external_ranks() {
   } else {
     s_board_path = key;
   }
-  int fd = open(s_board_path.c_str(), O_RDWR | O_CREAT, 0600);
-  if (fd < 0) terminate("attach_external_ranks: cannot open " + s_board_path, 1);
-  if (ftruncate(fd, sizeof(SharedBoard)) != 0) terminate("attach_external_ranks: ftruncate failed", 1);
-  void* m = mmap(nullptr, sizeof(SharedBoard), PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
-  close(fd);
-  if (m == MAP_FAILED) terminate("attach_external_ranks: mmap failed", 1);
-  s_board = reinterpret_cast<SharedBoard*>(m);  // a fresh file is all zeros: a valid initial board
   set_world((int)rank, (int)size);
-  return true;
+  const double deadline = wtime() + rendezvous_timeout();
+  if (rank == 0) {
+    // the creating rank: a fresh, exclusively created file (never follows a planted symlink, never reuses the
+    // contents a crashed launch left behind), initialised before the magic is published
+    int fd = -1;
+    for (int attempt = 0; attempt < 8 && fd < 0; ++attempt) {
+      fd = open(s_board_path.c_str(), O_RDWR | O_CREAT | O_EXCL | O_NOFOLLOW | O_CLOEXEC, 0600);
+      if (fd < 0 && errno == EEXIST) unlink(s_board_path.c_str());  // stale board of an earlier launch
+      else if (fd < 0) break;
+    }
+    if (fd < 0) terminate("attach_external_ranks: cannot create " + s_board_path + ": " + strerror(errno), 1);
+    if (ftruncate(fd, sizeof(SharedBoard)) != 0) terminate("attach_external_ranks: ftruncate failed", 1);
+    void* m = mmap(nullptr, sizeof(SharedBoard), PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (m == MAP_FAILED) terminate("attach_external_ranks: mmap failed", 1);
+    s_board = new (m) SharedBoard();  // barrier fields, id_ready and error_code start from zero
+    s_board->nranks = (int)size;
+    s_board->owner_pid = (int)getpid();
+    s_board->magic.store(kBoardMagic);
+    return true;
+  }
+  // the other ranks: wait for a board that is ours (regular file owned by this user, created by a LIVE rank 0 for
+  // the same number of ranks); anything else is a leftover that rank 0 is about to replace -- look again
+  for (;;) {
+    int fd = open(s_board_path.c_str(), O_RDWR | O_NOFOLLOW | O_CLOEXEC);
+    if (fd >= 0) {
+      struct stat st;
+      bool ok = fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_uid == geteuid() &&
+                (size_t)st.st_size >= sizeof(SharedBoard);
+      void* m = ok ? mmap(nullptr, sizeof(SharedBoard), PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0) : MAP_FAILED;
+      close(fd);
+      if (m != MAP_FAILED) {
+        SharedBoard* b = reinterpret_cast<SharedBoard*>(m);
+        if (b->magic.load() == kBoardMagic && b->nranks == (int)size && b->owner_pid > 0 && kill(b->owner_pid, 0) == 0) {
+          s_board = b;
+          return true;
+        }
+        munmap(m, sizeof(SharedBoard));
+      }
+    }
+    if (wtime() > deadline) rendezvous_failed("no board from rank 0");
+    usleep(2000);
+  }
 }
 
-// Sense-reversing barrier over the shared board (mpi_barrier).
+// Sense-reversing barrier over the shared board (mpi_barrier).  File-backed boards (external launcher) carry a
+// deadline: a rank that never arrives ends the job with a message instead of a silent hang.
 void world_barrier() {
   if (!s_board || s_size <= 1) return;
+  const bool timed = !s_board_path.empty();
+  const double deadline = timed ? wtime() + rendezvous_timeout() : 0.0;
   const int gen = s_board->barrier_gen.load();
   if (s_board->barrier_count.fetch_add(1) + 1 == s_size) {
     s_board->barrier_count.store(0);
     s_board->barrier_gen.fetch_add(1);
   } else {
-    while (s_board->barrier_gen.load() == gen) usleep(50);
+    while (s_board->barrier_gen.load() == gen) {
+      usleep(50);
+      if (timed && wtime() > deadline) rendezvous_failed("barrier");
+    }
+  }
+}
+
+// Wait until rank 0 has published the NCCL id on the board (the role of mpi_bcast), with the same deadline.
+void wait_for_nccl_id() {
+  if (!s_board) return;
+  const bool timed = !s_board_path.empty();
+  const double deadline = timed ? wtime() + rendezvous_timeout() : 0.0;
+  while (!s_board->id_ready.load()) {
+    usleep(100);
+    if (timed && wtime() > deadline) rendezvous_failed("NCCL id");
   }
 }
 

@@ -52,7 +52,7 @@ ekb200_ctx* b200_context(const ek_process_t& proc) {
       board->error_code.store(info);
       board->id_ready.store(1);
     } else {
-      while (!board->id_ready.load()) usleep(100);
+      wait_for_nccl_id();
       info = board->error_code.load();
     }
     if (info != 0) terminate("solver_b200: NCCL id could not be drawn", info);
@@ -183,9 +183,20 @@ void solve_with_b200(const ek_argument_t& arg, int64_t n, const ek_process_t& pr
                             generalized ? matrix_B->value.data() : v_dummy, ep.values.data(), ep.Vectors, ep.lld);
     replay_events(ctx);
   }
+  if (info > EKB200_WARN_STEIN && info < EKB200_FAIL_STEDC) {
+    // inverse iteration left some eigenvectors unconverged: the reference only REPORTS pdsyevx's IFAIL and carries on
+    // (solver_scalapack_select.f90:61-67); the library has returned all results
+    if (check_master()) {
+      printf("[Warning] eigen_solver_b200_select: inverse iteration did not converge for %d of %d requested eigenvectors\n",
+             info - EKB200_WARN_STEIN, (int)n_vec);
+      fflush(stdout);
+    }
+    info = 0;
+  }
   if (info != 0) {
-    // same reporting as generalized_to_standard.f90:25-30
+    // same reporting as generalized_to_standard.f90:25-30; the routine name follows the range of the code
     if (generalized && info > 0 && info <= n) check(info, "pdpotrf");
+    if (info > EKB200_FAIL_STEDC && info < 1000000) check(info - EKB200_FAIL_STEDC, "pdstedc");
     check(info, generalized ? "ekb200_sygvd" : "ekb200_syevd");
   }
   add_event(generalized ? "solve_with_general_b200:wall" : "eigen_solver_b200:wall", wtime() - time_start);

@@ -118,6 +118,26 @@ int ekb200_set_option(ekb200_ctx* h, const char* key, int64_t value) {
     ctx->reduction = (int)value;
     return 0;
   }
+  if (!strcmp(key, "sb2st_variant")) {  // 1: register-resident lag-2 bulge chasing (default); 0: round-1 kernel
+    if (value != 0 && value != 1) return -3;
+    ctx->sb2st_variant = (int)value;
+    return 0;
+  }
+  if (!strcmp(key, "sb2st_warps")) {  // warps per CTA of the register-resident bulge-chasing kernel
+    if (value != 8 && value != 16) return -3;
+    ctx->sb2st_warps = (int)value;
+    return 0;
+  }
+  if (!strcmp(key, "sb2st_rwarp")) {  // dedicated reflector warp of the bulge-chasing kernel (tuning)
+    if (value != 0 && value != 1) return -3;
+    ctx->sb2st_rwarp = (int)value;
+    return 0;
+  }
+  if (!strcmp(key, "sb2st_cps")) {  // cap on resident bulge-chasing CTAs per SM (tuning; 0 = no cap)
+    if (value < 0 || value > 4) return -3;
+    ctx->sb2st_cps = (int)value;
+    return 0;
+  }
   if (!strcmp(key, "q2_kc")) {
     if (value != 0 && value != 1004 && value != 1008 && value != 1012 && (value < 64 || value > 128 || value % 16))
       return -3;
@@ -214,19 +234,30 @@ int ekb200_coo_to_dense(ekb200_ctx* h, int64_t n, int64_t nnz, const int32_t* ho
   if (lda < n) return -7;
   EKB_TRY(set_zero(ctx, dev_A, lda, n, n));
   if (nnz == 0) return 0;
-  // "last duplicate wins" (distribute_matrix.f90:411-418 executes pdelset sequentially): chunks are
-  // uploaded and scattered in order; inside a chunk duplicates are not expected in symmetric files.
+  // "last duplicate wins", symmetric (distribute_matrix.f90:411-418 executes pdelset sequentially): resolved
+  // deterministically on the device by coo_scatter (fill.cu)
   int32_t* d_ij = nullptr;
   double* d_v = nullptr;
-  EKB_TRY(ctx_alloc(ctx, (void**)&d_ij, (size_t)nnz * 2 * sizeof(int32_t)));
-  EKB_TRY(ctx_alloc(ctx, (void**)&d_v, (size_t)nnz * sizeof(double)));
-  EKB_CUDA(cudaMemcpyAsync(d_ij, host_ij, (size_t)nnz * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
-  EKB_CUDA(cudaMemcpyAsync(d_v, host_v, (size_t)nnz * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  EKB_TRY(coo_scatter(ctx, dev_A, lda, n, nnz, d_ij, d_v));
-  EKB_CUDA(cudaStreamSynchronize(ctx->stream));
-  ctx_free(ctx, d_ij);
-  ctx_free(ctx, d_v);
-  return 0;
+  auto cleanup = [&]() {
+    cudaStreamSynchronize(ctx->stream);
+    ctx_free(ctx, d_ij);
+    ctx_free(ctx, d_v);
+  };
+  int rc = ctx_alloc(ctx, (void**)&d_ij, (size_t)nnz * 2 * sizeof(int32_t));
+  if (!rc) rc = ctx_alloc(ctx, (void**)&d_v, (size_t)nnz * sizeof(double));
+  if (!rc) {
+    cudaError_t ce = cudaMemcpyAsync(d_ij, host_ij, (size_t)nnz * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (ce == cudaSuccess)
+      ce = cudaMemcpyAsync(d_v, host_v, (size_t)nnz * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    if (ce != cudaSuccess) {
+      ctx->last_cuda = ce;
+      ctx->last_error = std::string("ekb200_coo_to_dense: ") + cudaGetErrorString(ce);
+      rc = EKB_ERR_CUDA;
+    }
+  }
+  if (!rc) rc = coo_scatter(ctx, dev_A, lda, n, nnz, d_ij, d_v);
+  cleanup();
+  return rc;
 }
 
 int ekb200_fill_synthetic(ekb200_ctx* h, int64_t n, uint64_t seed, double offdiag_div, int diag_mode,

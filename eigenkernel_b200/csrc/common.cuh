@@ -18,6 +18,11 @@ typedef long long i64;
 
 // LAPACK-style info codes of the C-ABI: 0 ok, <0 argument -i illegal, >0 numerical failure.
 // Internal CUDA failures map to EKB_ERR_CUDA.
+// Whole-solve drivers tell their positive codes apart by range: 1..n = order of the non-positive leading minor of the
+// Cholesky step (info(pdpotrf)); EKB_WARN_STEIN + k = k eigenvectors did not converge in inverse iteration (a WARNING:
+// the results were computed and returned, like pdsyevx's IFAIL); EKB_FAIL_STEDC + k = k leaf problems of the divide
+// and conquer failed (info(pdstedc)).
+enum { EKB_WARN_STEIN = 500000, EKB_FAIL_STEDC = 600000 };
 enum { EKB_ERR_CUDA = 1000001, EKB_ERR_NOMEM = 1000002, EKB_ERR_INTERNAL = 1000003, EKB_ERR_COMM = 1000004 };
 
 struct Event {
@@ -47,6 +52,10 @@ struct Ctx {
   int band = 64;                      // b: half bandwidth of the two-stage reduction
   int select_method = 0;              // -n solvers: 0 auto (D&C unless its workspaces do not fit), 1 D&C, 2 bisection + inverse iteration
   int reduction = 0;                  // 0: blocked pdsygst-style reduction; 1: explicit inverse (ELPA-style)
+  int sb2st_variant = 1;              // 1: register-resident lag-2 kernel (round 2); 0: the round-1 shared-memory kernel
+  int sb2st_warps = 8;                // compute warps per CTA of the register-resident kernel (8 | 16)
+  int sb2st_rwarp = 1;                // 1: one extra warp forms the reflectors beside the updates; 0: warp 0 does
+  int sb2st_cps = 0;                  // cap on resident CTAs per SM (0 = what the occupancy calculator allows)
   int q2_kc = 0;                      // columns of Z per CTA in apply_q2 (0 = choose; 64|80|96|112|128)
   // stage timers
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;

@@ -80,22 +80,60 @@ int set_identity(Ctx* ctx, double* A, i64 lda, i64 n) {
   return 0;
 }
 
-// COO (1-based, Fortran suffix(2,nnz)) -> dense, mirrored when i != j (distribute_matrix.f90:411-418).
-// "Last duplicate wins" is honoured by a single-thread-per-duplicate-free assumption: MatrixMarket
-// symmetric files store each entry once; duplicates are resolved on the host before upload.
-__global__ void coo_scatter_kernel(double* __restrict__ A, i64 lda, i64 n, i64 nnz, const int32_t* __restrict__ ij,
-                                   const double* __restrict__ v) {
+// COO (1-based, Fortran suffix(2,nnz)) -> dense, mirrored when i != j.  The reference scatters with a sequential
+// pdelset loop (distribute_matrix.f90:411-418): when an element occurs more than once -- repeated, or once as (i,j) and
+// once as (j,i) -- the LAST entry of the file wins, for both triangles.  One thread per entry cannot just store: the
+// result would depend on the order the threads happen to run in.  Three passes, deterministic:
+//   1. every entry takes part in an atomicMax of (its index + 1) at the canonical position (max(i,j), min(i,j)) of
+//      the zeroed matrix itself (positive doubles order like their bit patterns, so the matrix doubles as the index
+//      table: no n x n workspace);
+//   2. an entry whose index is the one that survived is the winner of its element (flag array);
+//   3. the winners store their value at (i,j) and (j,i).
+__global__ void coo_claim_kernel(double* __restrict__ A, i64 lda, i64 n, i64 nnz, const int32_t* __restrict__ ij) {
   i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nnz) return;
   i64 i = ij[2 * t] - 1, j = ij[2 * t + 1] - 1;
   if (i < 0 || j < 0 || i >= n || j >= n) return;
+  const i64 r = i > j ? i : j, c = i > j ? j : i;
+  atomicMax(reinterpret_cast<unsigned long long*>(A + c * lda + r), (unsigned long long)__double_as_longlong((double)(t + 1)));
+}
+__global__ void coo_winner_kernel(const double* __restrict__ A, i64 lda, i64 n, i64 nnz, const int32_t* __restrict__ ij,
+                                  unsigned char* __restrict__ win) {
+  i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nnz) return;
+  i64 i = ij[2 * t] - 1, j = ij[2 * t + 1] - 1;
+  unsigned char w = 0;
+  if (!(i < 0 || j < 0 || i >= n || j >= n)) {
+    const i64 r = i > j ? i : j, c = i > j ? j : i;
+    w = A[c * lda + r] == (double)(t + 1);
+  }
+  win[t] = w;
+}
+__global__ void coo_store_kernel(double* __restrict__ A, i64 lda, i64 nnz, const int32_t* __restrict__ ij,
+                                 const double* __restrict__ v, const unsigned char* __restrict__ win) {
+  i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nnz || !win[t]) return;
+  i64 i = ij[2 * t] - 1, j = ij[2 * t + 1] - 1;
   A[j * lda + i] = v[t];
   if (i != j) A[i * lda + j] = v[t];
 }
+// A must be zero on entry (ekb200_coo_to_dense zeroes it).
 int coo_scatter(Ctx* ctx, double* A, i64 lda, i64 n, i64 nnz, const int32_t* d_ij, const double* d_v) {
   if (nnz <= 0) return 0;
-  coo_scatter_kernel<<<cdiv(nnz, 256), 256, 0, ctx->stream>>>(A, lda, n, nnz, d_ij, d_v); EKB_COUNT_LAUNCH(ctx);
-  EKB_CUDA(cudaGetLastError());
+  unsigned char* win = nullptr;
+  EKB_TRY(ctx_alloc(ctx, (void**)&win, (size_t)nnz));
+  const int blocks = cdiv(nnz, 256);
+  coo_claim_kernel<<<blocks, 256, 0, ctx->stream>>>(A, lda, n, nnz, d_ij); EKB_COUNT_LAUNCH(ctx);
+  coo_winner_kernel<<<blocks, 256, 0, ctx->stream>>>(A, lda, n, nnz, d_ij, win); EKB_COUNT_LAUNCH(ctx);
+  coo_store_kernel<<<blocks, 256, 0, ctx->stream>>>(A, lda, nnz, d_ij, d_v, win); EKB_COUNT_LAUNCH(ctx);
+  cudaError_t ce = cudaGetLastError();
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
+  ctx_free(ctx, win);
+  if (ce != cudaSuccess) {
+    ctx->last_cuda = ce;
+    ctx->last_error = std::string("coo_scatter: ") + cudaGetErrorString(ce);
+    return EKB_ERR_CUDA;
+  }
   return 0;
 }
 

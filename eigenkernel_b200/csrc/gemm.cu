@@ -221,6 +221,37 @@ gemm_kernel(GemmP p0, const GemmP* __restrict__ batch, int flags, int tri_keep, 
     cp_async_commit();
   }
 
+  // Accumulate-into-C updates (beta != 0) with alpha = +-1 -- every trailing update of the library (Cholesky, sygst,
+  // the K = 2b SYR2K of dense-to-band, Q1, the triangular solves) -- start from acc = alpha beta C: the loads of C are
+  // issued here, right behind the pipeline prologue, and land while the first operand tiles are in flight, and the
+  // epilogue becomes store-only.  (The round-1 epilogue read each C element just before writing it: loads could not be
+  // hoisted over the preceding stores, so a tile paid 32 dependent L2 round trips -- more than its whole main loop when
+  // K = 128.)  Exact: alpha (alpha beta C + A B) = beta C + alpha A B for alpha = +-1.
+  const bool cvec = (((uintptr_t)C & 15) == 0) && ((ldc & 1) == 0);
+  if (beta != 0.0 && (alpha == 1.0 || alpha == -1.0)) {
+    const double sc = alpha * beta;
+#pragma unroll
+    for (int j = 0; j < NI; ++j) {
+      const int col = n0 + wn * WN + j * 8 + lq;
+      if (col >= p.n) continue;
+#pragma unroll
+      for (int i = 0; i < MI; ++i) {
+        const int row = m0 + wm * WM + i * 8 + 2 * lr;
+        if (row >= p.m) continue;
+        const double* cp = C + (i64)col * ldc + row;
+        if (row + 1 < p.m && cvec) {
+          const double2 old = __ldcg(reinterpret_cast<const double2*>(cp));
+          acc[i][j][0] = sc * old.x;
+          acc[i][j][1] = sc * old.y;
+        } else {
+          acc[i][j][0] = sc * cp[0];
+          if (row + 1 < p.m) acc[i][j][1] = sc * cp[1];
+        }
+      }
+    }
+    beta = 0.0;
+  }
+
   // thread offsets of the fragment loads for either layout of each operand
   const int a_t_km = (wm * WM + lq) * LDK + lr, a_t_mn = (wm * WM + lq) + lr * (BM + 4);
   const int b_t = b_kmajor ? (wn * WN + lq) * LDK + lr : (wn * WN + lq) + lr * (BN + 4);
@@ -247,32 +278,42 @@ gemm_kernel(GemmP p0, const GemmP* __restrict__ batch, int flags, int tri_keep, 
   }
   cp_async_wait<0>();
 
-  // epilogue: thread owns C(m0w + i*8 + 2*lr + {0,1}, n0w + j*8 + lq)
-  const bool cvec = (((uintptr_t)C & 15) == 0) && ((ldc & 1) == 0);
+  // epilogue: thread owns C(m0w + i*8 + 2*lr + {0,1}, n0w + j*8 + lq).  When C is still to be read (beta != 0 with
+  // a general alpha) the MI loads of a column are issued together, ahead of that column's stores.
 #pragma unroll
   for (int j = 0; j < NI; ++j) {
     const int col = n0 + wn * WN + j * 8 + lq;
     if (col >= p.n) continue;
+    double2 old[MI];
+    if (beta != 0.0) {
+#pragma unroll
+      for (int i = 0; i < MI; ++i) {
+        const int row = m0 + wm * WM + i * 8 + 2 * lr;
+        old[i] = make_double2(0.0, 0.0);
+        if (row >= p.m) continue;
+        const double* cp = C + (i64)col * ldc + row;
+        if (row + 1 < p.m && cvec) old[i] = *reinterpret_cast<const double2*>(cp);
+        else {
+          old[i].x = cp[0];
+          if (row + 1 < p.m) old[i].y = cp[1];
+        }
+      }
+    }
 #pragma unroll
     for (int i = 0; i < MI; ++i) {
       const int row = m0 + wm * WM + i * 8 + 2 * lr;
       if (row >= p.m) continue;
       double* cp = C + (i64)col * ldc + row;
       double v0 = alpha * acc[i][j][0], v1 = alpha * acc[i][j][1];
+      if (beta != 0.0) {
+        v0 += beta * old[i].x;
+        v1 += beta * old[i].y;
+      }
       if (row + 1 < p.m && cvec) {
-        if (beta != 0.0) {
-          double2 old = *reinterpret_cast<const double2*>(cp);
-          v0 += beta * old.x;
-          v1 += beta * old.y;
-        }
         *reinterpret_cast<double2*>(cp) = make_double2(v0, v1);
       } else {
-        if (beta != 0.0) v0 += beta * cp[0];
         cp[0] = v0;
-        if (row + 1 < p.m) {
-          if (beta != 0.0) v1 += beta * cp[1];
-          cp[1] = v1;
-        }
+        if (row + 1 < p.m) cp[1] = v1;
       }
     }
   }

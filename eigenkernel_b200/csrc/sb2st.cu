@@ -226,6 +226,377 @@ __global__ void __launch_bounds__(4 * B, 2) sb2st_kernel(double* __restrict__ AB
   }
 }
 
+
+// ------------------------------------------------------------------------------------------ register-resident kernel
+// Second-generation bulge chasing (round 2).  Same sweep-per-CTA pipeline, same band / V2 / TAU2 layouts, but built
+// for LATENCY: the per-sweep critical path is what bounds this stage (n sweeps, each waiting for its predecessor),
+// so every task is arranged as two short all-thread phases around two CTA barriers, nothing in the window ever
+// lives in shared memory, and a sweep may follow its predecessor at a distance of TWO tasks instead of three.
+//
+//   * Data layout in registers: warp w owns columns [w CW, (w+1) CW) of every b x b block, lane l owns rows l (and
+//     l + 32 for b = 64): all band loads / stores are 256-byte contiguous per warp instruction, each element is
+//     loaded once and stored once.  The B block of task t stays in registers and IS the L block of task t+1.
+//   * Task t, phase A (needs only v_t): left-apply on the L block (column dots by a transposed butterfly of warp
+//     shuffles, rank-1 update, store) -- this overlaps the wait for sweep s-1; then the dependency poll (one
+//     ld.acquire per warp), the loads of D_t (lower triangle) and B_t, and the partial dots of the symmetric
+//     mat-vec p = tau D v and of u = tau B v (row parts through shared memory, column part by shuffles).
+//   * Phase B (after the one barrier): every warp redundantly finishes p, sigma = p.v and w = p - tau/2 sigma v
+//     (bit-identical in all warps), applies D -= v w^T + w v^T (lower part) and B -= u v^T in registers, stores D,
+//     and warp 0 forms the NEXT reflector from column 0 of the new B block (look-ahead).
+//   * Look-ahead makes the distance 2: sweep s+1 needs from task t+2 of sweep s exactly one element, the beta of that
+//     task's reflector; task t+1 now computes it and writes it into the band before its completion is published.
+//     (Consequently the L block is stored WITHOUT its (0,0) element: by then a later sweep may have consumed and
+//     overwritten it.)  The schedule, including every read/write overlap between unordered tasks, is replayed on the
+//     CPU in tests/test_host_sb2st_schedule.py.
+//   * Publication: all stores of task t are issued before the barrier that opens task t+1; thread 0 then does one
+//     st.release.gpu of the task count.  Consumers poll with ld.relaxed.gpu and read the band with ld.cg.
+// Progress counters are polled with a strong relaxed load: ld.acquire would add an L1 invalidation (CCTL.IVALL) to
+// every iteration of the spin loop -- 16 % of all stall samples in the first capture of this kernel -- and buys
+// nothing here: every band element is read with ld.cg (L2, the point of coherence the counter itself is read from),
+// so there is no stale L1 line to drop; the loads are issued after the loop exits (control dependency, in-order issue).
+__device__ __forceinline__ int ld_poll_gpu(const int* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ double shx(double x, int m) { return __shfl_xor_sync(0xffffffffu, x, m); }
+__device__ __forceinline__ double shi(double x, int src) { return __shfl_sync(0xffffffffu, x, src); }
+
+// y[c] <- sum over the 32 lanes of y[c], for all c, in every lane (bit-identical in all lanes): reduce-scatter by a
+// transposed butterfly (CW/2 + CW/4 + .. exchanges), plain butterfly on the one remaining value, all-gather.
+template <int CW>
+__device__ __forceinline__ void warp_allreduce_cols(double (&y)[CW], int lane) {
+  static_assert(CW == 8 || CW == 4, "columns per warp");
+  if constexpr (CW == 8) {
+    double a[4], b2[2], c1;
+    const bool h4 = lane & 16, h3 = lane & 8, h2 = lane & 4;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) a[k] = (h4 ? y[k + 4] : y[k]) + shx(h4 ? y[k] : y[k + 4], 16);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) b2[k] = (h3 ? a[k + 2] : a[k]) + shx(h3 ? a[k] : a[k + 2], 8);
+    c1 = (h2 ? b2[1] : b2[0]) + shx(h2 ? b2[0] : b2[1], 4);
+    c1 += shx(c1, 2);
+    c1 += shx(c1, 1);
+    // this lane now holds the total of column 4 bit4 + 2 bit3 + bit2
+#pragma unroll
+    for (int k = 0; k < 8; ++k) y[k] = shi(c1, ((k >> 2) & 1) * 16 + ((k >> 1) & 1) * 8 + (k & 1) * 4);
+  } else {
+    double a[2], c1;
+    const bool h4 = lane & 16, h3 = lane & 8;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) a[k] = (h4 ? y[k + 2] : y[k]) + shx(h4 ? y[k] : y[k + 2], 16);
+    c1 = (h3 ? a[1] : a[0]) + shx(h3 ? a[0] : a[1], 8);
+    c1 += shx(c1, 4);
+    c1 += shx(c1, 2);
+    c1 += shx(c1, 1);
+    // this lane now holds the total of column 2 bit4 + bit3
+#pragma unroll
+    for (int k = 0; k < 4; ++k) y[k] = shi(c1, ((k >> 1) & 1) * 16 + (k & 1) * 8);
+  }
+}
+
+__device__ __forceinline__ double warp_allreduce_sum(double x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += shx(x, o);
+  return x;
+}
+
+// Householder reflector (dlarfg convention) of the vector whose element `row = lane + 32 h` is x[h], rows < nrow
+// valid; all lanes return the same tau and beta; v has the leading 1 explicit and zeros beyond nrow.
+template <int RH>
+__device__ __forceinline__ void warp_reflector(const double (&x)[RH], int nrow, int lane, double (&v)[RH], double& tau,
+                                               double& beta) {
+  double sq = 0.0;
+#pragma unroll
+  for (int h = 0; h < RH; ++h) {
+    const int row = lane + 32 * h;
+    if (row >= 1 && row < nrow) sq += x[h] * x[h];
+  }
+  sq = warp_allreduce_sum(sq);
+  const double alpha = shi(x[0], 0);
+  double sc;
+  if (sq == 0.0) {
+    beta = alpha; tau = 0.0; sc = 0.0;
+  } else {
+    beta = -copysign(sqrt(alpha * alpha + sq), alpha);
+    tau = (beta - alpha) / beta;
+    sc = 1.0 / (alpha - beta);
+  }
+#pragma unroll
+  for (int h = 0; h < RH; ++h) {
+    const int row = lane + 32 * h;
+    v[h] = (row == 0) ? 1.0 : (row < nrow ? x[h] * sc : 0.0);
+  }
+}
+
+// TRACE (development only, EKB200_SB2ST_TRACE=<file>): lane 0 of warps 0 and 1 of one CTA record clock64() at the
+// phase boundaries of its first SB2ST_TRACE_TASKS tasks; the production instantiation carries none of it.
+constexpr int SB2ST_TRACE_TASKS = 4096, SB2ST_TRACE_PTS = 8, SB2ST_TRACE_CTA = 5;
+// RW: one extra warp (warp NW) does nothing but form reflectors, so that the next reflector (norm, square root, two
+// divisions: the longest scalar chain of a task) runs BESIDE the rank-1/2 updates of the compute warps instead of
+// after warp 0's share of them.
+template <int B, int NW, bool RW, bool TRACE>
+__global__ void __launch_bounds__(32 * (NW + (RW ? 1 : 0)), ((NW <= 8 && !RW) ? 2 : 1))
+sb2st_reg_kernel(double* __restrict__ AB, i64 ldab, i64 n, double* __restrict__ V2, i64 ldv, double* __restrict__ TAU2,
+                 int ldtau, int* __restrict__ prog, long long* __restrict__ trace) {
+  constexpr int RH = B / 32;   // rows per lane
+  constexpr int CW = B / NW;   // columns per warp
+  constexpr int DONE = 0x3fffffff;
+  constexpr int RWARP = RW ? NW : 0;  // the warp that forms the reflectors
+  static_assert(B % 32 == 0 && B % NW == 0, "geometry");
+  __shared__ double s_v[2][B];
+  __shared__ double s_tau[2];
+  __shared__ double s_beta[2];
+  __shared__ double s_x[B];        // RW: column 0 of the B block as loaded (before the right-apply)
+  __shared__ double s_pu[NW][B];
+  __shared__ double s_pp[NW][B];
+  __shared__ double s_pc[B];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool compute = warp < NW;
+  const int j0 = warp * CW;
+  const i64 cstep = ldab - 1;  // one column to the right along a matrix row, in band storage
+  int trace_task = 0;
+  auto stamp = [&](int k, int slot) {
+    if constexpr (TRACE) {
+      if (blockIdx.x == SB2ST_TRACE_CTA && lane == 0 && trace_task < SB2ST_TRACE_TASKS)
+        trace[((i64)trace_task * 2 + slot) * SB2ST_TRACE_PTS + k] = clock64();
+    }
+  };
+  const int tslot = warp == 0 ? 0 : 1;
+  const bool traced = warp < 2;
+
+  for (i64 s = blockIdx.x; s <= n - 3; s += gridDim.x) {
+    const int ntask = sb2st_num_tasks(n, B, s);
+    // ---- prologue: reflector of task 0 from column s (needs task 0 of sweep s-1, look-ahead included)
+    if (warp == RWARP) {
+      if (s > 0) {
+        if (lane == 0) while (ld_poll_gpu(prog + (s - 1)) < 1) {}
+        __syncwarp();
+      }
+      const i64 r0 = s + 1;
+      const int nr = (int)min((i64)B, n - r0);
+      double x[RH], v[RH], tau, beta;
+#pragma unroll
+      for (int h = 0; h < RH; ++h) {
+        const int row = lane + 32 * h;
+        x[h] = row < nr ? __ldcg(AB + s * ldab + 1 + row) : 0.0;
+      }
+      warp_reflector<RH>(x, nr, lane, v, tau, beta);
+#pragma unroll
+      for (int h = 0; h < RH; ++h) {
+        const int row = lane + 32 * h;
+        s_v[0][row] = v[h];
+        if (row < nr) {
+          V2[s * ldv + r0 + row] = v[h];
+          AB[s * ldab + 1 + row] = (row == 0) ? beta : 0.0;
+        }
+      }
+      if (lane == 0) {
+        s_tau[0] = tau;
+        TAU2[s * (i64)ldtau] = tau;
+      }
+    }
+    double Bt[RH][CW];
+#pragma unroll
+    for (int h = 0; h < RH; ++h)
+#pragma unroll
+      for (int c = 0; c < CW; ++c) Bt[h][c] = 0.0;
+
+    for (int t = 0; t < ntask; ++t) {
+      const int cur = t & 1;
+      __syncthreads();  // v_t, tau_t visible; every store of task t-1 has been issued
+      if (tid == 0 && t > 0) st_release_gpu(prog + s, t);  // tasks 0 .. t-1 complete (and beta_t is in the band)
+      if (traced) stamp(0, tslot);
+      const double tau = s_tau[cur];
+      const i64 r0 = s + 1 + (i64)t * B;
+      const int nr = (int)min((i64)B, n - r0);                             // rows of R (>= 2)
+      const int nr2 = (int)max((i64)0, min((i64)B, n - (r0 + B)));         // rows of the block below
+      const bool last = t + 1 >= ntask;
+      double vr[RH];
+#pragma unroll
+      for (int h = 0; h < RH; ++h) vr[h] = s_v[cur][lane + 32 * h];
+      if (compute) {
+        const double* vc = &s_v[cur][j0];  // v at this warp's columns: broadcast reads where needed (keeps registers free)
+        // ---- L block (the B block of task t-1, columns R - B, rows R): H L, store.  Needs nothing from sweep s-1.
+        if (t > 0) {
+          if (RW && warp == 0) {  // column 0 became beta e1 when the reflector was formed (by the reflector warp)
+            const double bt = s_beta[cur];
+#pragma unroll
+            for (int h = 0; h < RH; ++h) Bt[h][0] = (lane + 32 * h == 0) ? bt : 0.0;
+          }
+          double y[CW];
+#pragma unroll
+          for (int c = 0; c < CW; ++c) {
+            y[c] = 0.0;
+#pragma unroll
+            for (int h = 0; h < RH; ++h) y[c] = fma(vr[h], Bt[h][c], y[c]);
+          }
+          warp_allreduce_cols<CW>(y, lane);
+#pragma unroll
+          for (int c = 0; c < CW; ++c) y[c] *= tau;
+          if (warp == 0) y[0] = 0.0;  // column 0 already is beta e1
+          double* lp = AB + (r0 - B + j0) * ldab + (B - j0) + lane;  // element (row = lane, col = j0)
+#pragma unroll
+          for (int c = 0; c < CW; ++c)
+#pragma unroll
+            for (int h = 0; h < RH; ++h) {
+              const int row = lane + 32 * h;
+              Bt[h][c] = fma(-vr[h], y[c], Bt[h][c]);
+              // (0,0) = beta went to the band with the look-ahead; a later sweep may already have overwritten it
+              if (row < nr && !(warp == 0 && c == 0 && row == 0)) lp[c * cstep + 32 * h] = Bt[h][c];
+            }
+        }
+        if (traced) stamp(1, tslot);
+        // ---- wait for sweep s-1: tasks 0 .. t+1 complete
+        if (s > 0) {
+          if (lane == 0) while (ld_poll_gpu(prog + (s - 1)) < t + 2) {}
+          __syncwarp();
+        }
+        if (traced) stamp(2, tslot);
+        // ---- D block (lower triangle of A(R,R)) and B block (A(R+B, R))
+        double Dt[RH][CW];
+        double* dp = AB + (r0 + j0) * ldab - j0 + lane;  // D element (row = lane, col = j0); B element: B rows below
+#pragma unroll
+        for (int c = 0; c < CW; ++c)
+#pragma unroll
+          for (int h = 0; h < RH; ++h) {
+            const int row = lane + 32 * h, col = j0 + c;
+            Dt[h][c] = (col < nr && row >= col && row < nr) ? __ldcg(dp + c * cstep + 32 * h) : 0.0;
+            Bt[h][c] = (col < nr && row < nr2) ? __ldcg(dp + c * cstep + 32 * h + B) : 0.0;
+          }
+        // ---- partial dots: u = tau B v (rows), p = tau D v (rows from the lower triangle, columns from its transpose)
+        {
+          double pu[RH], pp[RH], pcq[CW];
+#pragma unroll
+          for (int h = 0; h < RH; ++h) {
+            pu[h] = 0.0;
+            pp[h] = 0.0;
+#pragma unroll
+            for (int c = 0; c < CW; ++c) {
+              pu[h] = fma(Bt[h][c], vc[c], pu[h]);
+              pp[h] = fma(Dt[h][c], vc[c], pp[h]);
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < CW; ++c) {
+            pcq[c] = 0.0;
+#pragma unroll
+            for (int h = 0; h < RH; ++h)
+              if (lane + 32 * h != j0 + c) pcq[c] = fma(Dt[h][c], vr[h], pcq[c]);  // strictly lower part, transposed
+          }
+          if constexpr (TRACE) {
+            if (pu[0] + pp[0] + pcq[0] == 1.2345e300) trace[0] = 0;  // consume the loads before the stamp
+            if (traced) stamp(3, tslot);
+          }
+          warp_allreduce_cols<CW>(pcq, lane);
+#pragma unroll
+          for (int h = 0; h < RH; ++h) {
+            s_pu[warp][lane + 32 * h] = pu[h];
+            s_pp[warp][lane + 32 * h] = pp[h];
+            if (RW && warp == 0) s_x[lane + 32 * h] = Bt[h][0];
+          }
+#pragma unroll
+          for (int c = 0; c < CW; ++c)
+            if (lane == c) s_pc[j0 + c] = pcq[c];
+        }
+        if (traced) stamp(4, tslot);
+        __syncthreads();
+        if (traced) stamp(5, tslot);
+        // ---- every warp finishes u, p, sigma, w for its rows and columns (same operations in the same order: the
+        // redundant copies are bit-identical)
+        double u[RH], wv[RH], wc[CW];
+        {
+          double pv[RH];
+          double sig = 0.0;
+#pragma unroll
+          for (int h = 0; h < RH; ++h) {
+            const int row = lane + 32 * h;
+            double a = 0.0, q = 0.0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+              a += s_pu[w][row];
+              q += s_pp[w][row];
+            }
+            u[h] = tau * a;
+            pv[h] = tau * (q + s_pc[row]);
+            sig = fma(pv[h], vr[h], sig);
+          }
+          sig = warp_allreduce_sum(sig);
+#pragma unroll
+          for (int h = 0; h < RH; ++h) wv[h] = fma(-0.5 * tau * sig, vr[h], pv[h]);
+#pragma unroll
+          for (int c = 0; c < CW; ++c) {
+            const int col = j0 + c;
+            wc[c] = shi((RH == 2 && col >= 32) ? wv[RH - 1] : wv[0], col & 31);
+          }
+        }
+        // ---- D -= v w^T + w v^T (lower part, stored), B -= u v^T (kept: it is the L block of task t+1)
+#pragma unroll
+        for (int c = 0; c < CW; ++c)
+#pragma unroll
+          for (int h = 0; h < RH; ++h) {
+            const int row = lane + 32 * h, col = j0 + c;
+            double dv = fma(-vr[h], wc[c], Dt[h][c]);
+            dv = fma(-wv[h], vc[c], dv);
+            if (col < nr && row >= col && row < nr) dp[c * cstep + 32 * h] = dv;
+            Bt[h][c] = fma(-u[h], vc[c], Bt[h][c]);
+          }
+        if (traced) stamp(6, tslot);
+        if (last) {
+#pragma unroll
+          for (int c = 0; c < CW; ++c)
+#pragma unroll
+            for (int h = 0; h < RH; ++h) {
+              const int row = lane + 32 * h, col = j0 + c;
+              if (col < nr && row < nr2) dp[c * cstep + 32 * h + B] = Bt[h][c];
+            }
+        }
+      } else {
+        __syncthreads();  // the reflector warp has nothing to do before the partial dots are in shared memory
+      }
+      if (!last && warp == RWARP) {
+        // ---- look-ahead: reflector of task t+1 from column 0 of the new B block; its beta goes to the band now
+        double x[RH], vn[RH], taun, betan;
+        if (RW) {
+          const double v0 = s_v[cur][0];
+#pragma unroll
+          for (int h = 0; h < RH; ++h) {
+            const int row = lane + 32 * h;
+            double a = 0.0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) a += s_pu[w][row];
+            x[h] = fma(-(tau * a), v0, s_x[row]);  // the same expression the compute warps apply to column 0
+          }
+        } else {
+#pragma unroll
+          for (int h = 0; h < RH; ++h) x[h] = Bt[h][0];
+        }
+        warp_reflector<RH>(x, nr2, lane, vn, taun, betan);
+#pragma unroll
+        for (int h = 0; h < RH; ++h) {
+          const int row = lane + 32 * h;
+          s_v[cur ^ 1][row] = vn[h];
+          if (row < nr2) V2[s * ldv + r0 + B + row] = vn[h];
+          if (!RW) Bt[h][0] = (row == 0) ? betan : 0.0;
+        }
+        if (lane == 0) {
+          s_tau[cur ^ 1] = taun;
+          s_beta[cur ^ 1] = betan;
+          TAU2[s * (i64)ldtau + t + 1] = taun;
+          AB[r0 * ldab + B] = betan;
+        }
+        stamp(7, 0);
+      }
+      if constexpr (TRACE) ++trace_task;
+    }
+    __syncthreads();
+    if (tid == 0) st_release_gpu(prog + s, DONE);
+  }
+}
+
 __global__ void extract_de_kernel(const double* __restrict__ AB, i64 ldab, i64 n, double* __restrict__ d, double* __restrict__ e) {
   i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -237,10 +608,73 @@ int sb2st_max_tasks(i64 n, int b) { return (int)(n / b) + 2; }
 
 // AB: ldab >= 2b rows (rows b+1.. must be zero on entry).  V2: n x (n-2 or more), ldv; TAU2: ldtau x (n-2).
 // d (n), e (n-1) receive the tridiagonal.  prog: int workspace of n entries.
+template <int B, int NW, bool RW, bool TRACE = false>
+static int sb2st_reg_launch(Ctx* ctx, i64 n, double* AB, i64 ldab, double* V2, i64 ldv, double* TAU2, int ldtau, int* prog,
+                            long long* trace = nullptr) {
+  auto kern = sb2st_reg_kernel<B, NW, RW, TRACE>;
+  constexpr int threads = 32 * (NW + (RW ? 1 : 0));
+  int per_sm = 0;
+  EKB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0));
+  if (ctx->sb2st_cps > 0 && per_sm > ctx->sb2st_cps) per_sm = ctx->sb2st_cps;
+  i64 G = (i64)per_sm * ctx->num_sms;
+  if (G < 1) return EKB_ERR_INTERNAL;
+  // a sweep follows its predecessor at a distance of 2 tasks: more than ntask(0)/2 + 2 CTAs would only wait
+  const i64 maxuse = (n / B) / 2 + 2;
+  if (G > maxuse) G = maxuse;
+  if (G > n - 2) G = n - 2;
+  void* args[] = {(void*)&AB, (void*)&ldab, (void*)&n, (void*)&V2, (void*)&ldv, (void*)&TAU2, (void*)&ldtau, (void*)&prog,
+                  (void*)&trace};
+  // all CTAs must be co-resident (spin-wait dependencies): the cooperative launch enforces it
+  EKB_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3((unsigned)G), dim3(threads), args, 0, ctx->stream));
+  EKB_COUNT_LAUNCH(ctx);
+  return 0;
+}
+
+template <bool TRACE>
+static int sb2st_reg_dispatch(Ctx* ctx, i64 n, int b, double* AB, i64 ldab, double* V2, i64 ldv, double* TAU2, int ldtau,
+                              int* prog, long long* trace) {
+  const bool wide = ctx->sb2st_warps == 16, rw = ctx->sb2st_rwarp != 0;
+  if (b == 64) {
+    if (wide) return rw ? sb2st_reg_launch<64, 16, true, TRACE>(ctx, n, AB, ldab, V2, ldv, TAU2, ldtau, prog, trace)
+                        : sb2st_reg_launch<64, 16, false, TRACE>(ctx, n, AB, ldab, V2, ldv, TAU2, ldtau, prog, trace);
+    return rw ? sb2st_reg_launch<64, 8, true, TRACE>(ctx, n, AB, ldab, V2, ldv, TAU2, ldtau, prog, trace)
+              : sb2st_reg_launch<64, 8, false, TRACE>(ctx, n, AB, ldab, V2, ldv, TAU2, ldtau, prog, trace);
+  }
+  return rw ? sb2st_reg_launch<32, 8, true, TRACE>(ctx, n, AB, ldab, V2, ldv, TAU2, ldtau, prog, trace)
+            : sb2st_reg_launch<32, 8, false, TRACE>(ctx, n, AB, ldab, V2, ldv, TAU2, ldtau, prog, trace);
+}
+
+// AB: ldab >= 2b rows (rows b+1.. must be zero on entry).  V2: n x (n-2 or more), ldv; TAU2: ldtau x (n-2).
+// d (n), e (n-1) receive the tridiagonal.  prog: int workspace of n entries.
 int sb2st(Ctx* ctx, i64 n, int b, double* AB, i64 ldab, double* V2, i64 ldv, double* TAU2, int ldtau, int* prog,
           double* d, double* e) {
   if (n <= 0) return 0;
-  if (n >= 3) {
+  if (n >= 3 && ctx->sb2st_variant != 0) {
+    EKB_CUDA(cudaMemsetAsync(prog, 0, (size_t)n * sizeof(int), ctx->stream));
+    EKB_TRY(prof_begin(ctx, PROF_SB2ST, 12.0 * b * (double)n * (double)n));  // effective bytes, SURVEY 8(d)
+    int rc;
+    const char* trace_path = getenv("EKB200_SB2ST_TRACE");
+    if (trace_path && *trace_path) {  // development aid: phase timestamps of one CTA -> binary file
+      const size_t cnt = (size_t)SB2ST_TRACE_TASKS * 2 * SB2ST_TRACE_PTS;
+      long long* dtr = nullptr;
+      EKB_TRY(ctx_alloc(ctx, (void**)&dtr, cnt * sizeof(long long)));
+      EKB_CUDA(cudaMemsetAsync(dtr, 0, cnt * sizeof(long long), ctx->stream));
+      rc = sb2st_reg_dispatch<true>(ctx, n, b, AB, ldab, V2, ldv, TAU2, ldtau, prog, dtr);
+      std::vector<long long> htr(cnt);
+      if (!rc && cudaMemcpyAsync(htr.data(), dtr, cnt * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream) == cudaSuccess &&
+          cudaStreamSynchronize(ctx->stream) == cudaSuccess) {
+        if (FILE* f = fopen(trace_path, "wb")) {
+          fwrite(htr.data(), sizeof(long long), cnt, f);
+          fclose(f);
+        }
+      }
+      ctx_free(ctx, dtr);
+    } else {
+      rc = sb2st_reg_dispatch<false>(ctx, n, b, AB, ldab, V2, ldv, TAU2, ldtau, prog, nullptr);
+    }
+    if (rc) return rc;
+    EKB_TRY(prof_end(ctx));
+  } else if (n >= 3) {
     EKB_CUDA(cudaMemsetAsync(prog, 0, (size_t)n * sizeof(int), ctx->stream));
     const size_t smem = (size_t)(3 * b * (b + 1) + 2 * b) * sizeof(double);
     int G = 0;

@@ -44,6 +44,7 @@ struct Scratch {
 // both back-transformations act on the slab only (no data-path collective).
 int syevd_dev(Ctx* ctx, i64 n, i64 nev, double* A, i64 lda, double* w, double* Z, i64 ldz, double* merge_flops) {
   if (n <= 0 || nev <= 0) return 0;
+  int stein_fail = 0;  // eigenvectors whose inverse iteration did not converge: a warning, the solve goes on
   const int b = ctx->band;
   std::vector<i64> zb;
   slab_bounds(nev, ctx->nranks, 128, zb);
@@ -108,7 +109,11 @@ int syevd_dev(Ctx* ctx, i64 n, i64 nev, double* A, i64 lda, double* w, double* Z
     int rc = stebz_stein(ctx, n, d, e, w, nev, c0, c0 + kc, Z, ldz, work);
     t.stop();
     sc.release(work);
-    if (rc) return rc;  // > 0: eigenvectors that failed to converge (IFAIL of pdsyevx)
+    // > 0: eigenvectors that failed dstein's growth test (IFAIL of pdsyevx).  The reference only reports this
+    // (solver_scalapack_select.f90:61-67) and carries on with what pdsyevx returned; so does this solver: the vectors
+    // are back-transformed like the others and the caller gets EKB_WARN_STEIN + count.
+    if (rc < 0 || rc >= 1000000) return rc;
+    stein_fail = rc;
   } else {
     StageTimer t(ctx, "eigen_solver_b200:stedc");
     void* work = nullptr;
@@ -126,6 +131,7 @@ int syevd_dev(Ctx* ctx, i64 n, i64 nev, double* A, i64 lda, double* w, double* Z
     }
     t.stop();
     sc.release(work);
+    if (rc > 0 && rc < 1000000) return EKB_FAIL_STEDC + rc;  // leaf problems that did not converge (info(pdstedc))
     if (rc) return rc;
   }
   {
@@ -147,7 +153,18 @@ int syevd_dev(Ctx* ctx, i64 n, i64 nev, double* A, i64 lda, double* w, double* Z
   }
   total.stop();
   EKB_CUDA(cudaGetLastError());
-  return 0;
+  if (ctx->nranks > 1 && use_stebz) {  // every rank reports the same count (sum over the slabs)
+    double* cnt = nullptr;
+    EKB_TRY(sc.get((void**)&cnt, 8 * sizeof(double)));
+    const double mine = (double)stein_fail;
+    EKB_CUDA(cudaMemcpyAsync(cnt, &mine, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    EKB_TRY(comm_allreduce_sum(ctx, cnt, 1));
+    double tot = 0.0;
+    EKB_CUDA(cudaMemcpyAsync(&tot, cnt, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    EKB_CUDA(cudaStreamSynchronize(ctx->stream));
+    stein_fail = (int)tot;
+  }
+  return stein_fail > 0 ? EKB_WARN_STEIN + stein_fail : 0;
 }
 
 // A, B full symmetric (B SPD) on the device.  B <- L (lower), A destroyed, w ascending, Z^T B Z = I.
@@ -193,7 +210,8 @@ int sygvd_dev(Ctx* ctx, i64 n, i64 nev, double* A, i64 lda, double* B, i64 ldb, 
     }
     red.stop();
   }
-  EKB_TRY(syevd_dev(ctx, n, nev, A, lda, w, Z, ldz, merge_flops));
+  int warn = syevd_dev(ctx, n, nev, A, lda, w, Z, ldz, merge_flops);
+  if (warn != 0 && !(warn > EKB_WARN_STEIN && warn < EKB_FAIL_STEDC)) return warn;
   {
     StageTimer t(ctx, "recovery_generalized_b200");
     std::vector<i64> zb;
@@ -208,7 +226,7 @@ int sygvd_dev(Ctx* ctx, i64 n, i64 nev, double* A, i64 lda, double* B, i64 ldb, 
   }
   total.stop();
   EKB_CUDA(cudaGetLastError());
-  return 0;
+  return warn;
 }
 
 }  // namespace ekb

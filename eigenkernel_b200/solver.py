@@ -19,6 +19,7 @@ from .app_io import EventLogger, MatrixInfo, SparseMat, TerminateError
 from .device import Context
 
 G_BLOCK_SIZE = 64          # global_variables.f90:5
+WARN_STEIN, FAIL_STEDC = 500000, 600000  # EKB200_WARN_STEIN / EKB200_FAIL_STEDC (include/ekb200.h)
 G_VERSION = "20160808"     # global_variables.f90:6
 
 STANDARD_SOLVERS = ("b200", "b200_select")
@@ -162,8 +163,19 @@ def eigen_solver(arg: Argument, matrix_A: SparseMat, matrix_B: SparseMat | None 
                     logger.add_event(name, 0.0, to_print=False)
                 logger.add_event(name, sec)
             logger.add_event("eigen_solver_b200:wall", wall)
+        if WARN_STEIN < info < FAIL_STEDC:
+            # pdsyevx's IFAIL report (solver_scalapack_select.f90:61-67): a warning, the results are complete
+            print(f"[Warning] eigen_solver_b200_select: inverse iteration did not converge for {info - WARN_STEIN} "
+                  f"of {n_vec} requested eigenvectors")
+            info = 0
         if info != 0:
-            routine = "pdpotrf" if generalized else "pdstedc"
+            # the routine name follows the RANGE of the code (include/ekb200.h), not the kind of problem
+            if FAIL_STEDC < info < 1000000:
+                routine, info = "pdstedc", info - FAIL_STEDC
+            elif generalized and 0 < info <= n:
+                routine = "pdpotrf"
+            else:
+                routine = "ekb200_sygvd_coo"
             print(f"info({routine}): {info}")
             raise TerminateError(f"eigen_solver: {routine} failed", info)
     finally:

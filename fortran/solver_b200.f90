@@ -30,6 +30,8 @@ module ek_solver_b200_m
   implicit none
   private
   public :: solve_with_b200, solve_with_general_b200, regrid_1xp
+  ! ranges of the positive status codes of the whole-solve entry points (include/ekb200.h)
+  integer(c_int), parameter :: ekb200_warn_stein = 500000_c_int, ekb200_fail_stedc = 600000_c_int
 
   interface
     integer(c_int) function ekb200_create(ctx, device) bind(C, name='ekb200_create')
@@ -199,11 +201,22 @@ contains
            int(eigenpairs%blacs%desc(lld_), c_int64_t))
     end if
     call replay_events(ctx)
+    if (info > ekb200_warn_stein .and. info < ekb200_fail_stedc) then
+      ! inverse iteration left some eigenvectors unconverged: like pdsyevx's IFAIL report
+      ! (solver_scalapack_select.f90:61-67) this is a warning, the library has returned all results
+      if (check_master()) then
+        print '("[Warning] eigen_solver_b200_select: inverse iteration did not converge for ", I0, " of ", I0, &
+             &" requested eigenvectors")', info - ekb200_warn_stein, n_vec
+      end if
+      info = 0
+    end if
     if (info /= 0) then
-      ! same reporting as generalized_to_standard.f90:25-30
+      ! same reporting as generalized_to_standard.f90:25-30; the routine name follows the range of the code
       if (check_master()) then
         if (present(matrix_B) .and. info > 0 .and. info <= n) then
           print '("info(pdpotrf): ", i0)', info
+        else if (info > ekb200_fail_stedc .and. info < 1000000) then
+          print '("info(pdstedc): ", i0)', info - ekb200_fail_stedc
         else
           print '("info(ekb200_sygvd_coo): ", i0)', info
         end if

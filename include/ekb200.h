@@ -9,6 +9,10 @@
  *  - every function returns a LAPACK-style `info`: 0 = ok, -i = i-th argument illegal, >0 = numerical
  *    failure (e.g. order of the non-positive leading minor in the Cholesky factorization);
  *    >= 1000001 = CUDA/internal failure (ekb200_strerror / ekb200_last_error give the text).
+ *    The whole-solve entry points tell their positive codes apart by range: 1..n = info(pdpotrf);
+ *    EKB200_WARN_STEIN + k = WARNING, k eigenvectors of a -n solve did not converge in inverse iteration, results
+ *    were still computed and returned (pdsyevx's IFAIL report, solver_scalapack_select.f90:61-67);
+ *    EKB200_FAIL_STEDC + k = k leaf problems of the divide and conquer failed (info(pdstedc)).
  *    The library never aborts and never prints; the Fortran wrapper turns info != 0 into
  *    `terminate(msg, info)` exactly as generalized_to_standard.f90:25-30 does.
  *  - matrices are column-major FP64; `ld*` are leading dimensions in elements; indices are int64.
@@ -23,6 +27,8 @@ extern "C" {
 #endif
 
 typedef struct ekb200_ctx ekb200_ctx;
+#define EKB200_WARN_STEIN 500000
+#define EKB200_FAIL_STEDC 600000
 
 /* ---- context (replaces setup_distribution, src/processes.f90:17-36: one context = one GPU "grid") */
 int ekb200_create(ekb200_ctx** ctx, int device);

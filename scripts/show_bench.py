@@ -23,6 +23,10 @@ for path in sys.argv[1:]:
         for f, ent in v.items():
             r = f" rate={ent['tflops_or_tbs']:.2f}" if "tflops_or_tbs" in ent else ""
             print(f"      [{st}] {f}: {ent['seconds']:.3f} s, {ent['launches']} launches{r}")
+    if d.get("acceptance"):
+        a = d["acceptance"]
+        print("   acceptance:", {k: a[k] for k in ("residual_max_over_A", "orthogonality_verifier",
+                                                   "xtbx_minus_identity_fro", "tolerance", "dlambda_vs_1gpu", "pass")})
     rf = d.get("roofline")
     if rf:
         print(f"   roofline: {rf['achieved']:.2f}/{rf['peak']:.2f} {rf['unit']} frac={rf['frac']:.3f} share={rf.get('share_of_step', 0):.3f}")

@@ -97,6 +97,33 @@ def test_synthetic_fill_is_bit_identical_to_oracle(ctx):
     assert np.array_equal(dB.download(), B)
 
 
+def test_coo_scatter_last_duplicate_wins_in_both_triangles(ctx):
+    """distribute_global_sparse_matrix (distribute_matrix.f90:411-418) is a sequential pdelset loop: when an element
+    occurs more than once -- repeated, or as (i,j) and later as (j,i) -- the LAST entry wins, in both triangles.  The
+    device scatter must reproduce that independently of thread order (run twice, bit-identical)."""
+    n, nnz = 97, 20000
+    rng = np.random.default_rng(5)
+    ij = rng.integers(1, n + 1, size=(nnz, 2)).astype(np.int32)   # heavy duplication, both orientations
+    v = rng.standard_normal(nnz)
+    ref = np.zeros((n, n), order="F")
+    for (i, j), x in zip(ij, v):   # the reference's loop
+        ref[i - 1, j - 1] = x
+        ref[j - 1, i - 1] = x
+    dA = ctx.matrix(n, n)
+    for _ in range(2):
+        assert ctx.call("ekb200_coo_to_dense", n, nnz, ij.ctypes.data, v.ctypes.data, dA.ptr, dA.ld) == 0
+        got = dA.download()
+        assert np.array_equal(got, ref)
+        assert np.array_equal(got, got.T)
+    # out-of-range entries are ignored, an empty list gives the zero matrix
+    bad = np.array([[0, 1], [n + 1, 2], [3, 3]], dtype=np.int32)
+    bv = np.array([1.0, 2.0, 3.0])
+    assert ctx.call("ekb200_coo_to_dense", n, 3, bad.ctypes.data, bv.ctypes.data, dA.ptr, dA.ld) == 0
+    got = dA.download()
+    assert got[2, 2] == 3.0 and np.count_nonzero(got) == 1
+    dA.free()
+
+
 def test_fp64_peak_probe(ctx):
     p = ctx.fp64_peak()
     print("FP64 peak:", p)

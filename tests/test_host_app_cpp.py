@@ -285,6 +285,67 @@ def test_cli_ranks_from_an_external_launcher(hooks, golden_dir, tmp_path):
     assert not board.exists()                             # rank 0 removes the board of the launch
 
 
+def test_cli_launcher_variables_alone_do_not_make_a_multi_rank_job(hooks, golden_dir, tmp_path):
+    """An sbatch script that runs the binary once (no srun) still has SLURM_PROCID / SLURM_NTASKS in its environment;
+    so does anything started under torchrun.  Attachment to an external launcher is opt-in (EKB200_EXTERNAL_RANKS=1 or
+    EKB200_RENDEZVOUS): without it the run is a plain single-rank run and must not wait for peers that do not exist."""
+    fa = os.path.join(golden_dir, "ELSES_MATRIX_VCNT400std_A.mtx")
+    env = dict(_clean_env(), SLURM_PROCID="0", SLURM_NTASKS="4", RANK="0", WORLD_SIZE="4")
+    r = subprocess.run([APP, "-s", "b200", "--dry-run", fa], cwd=tmp_path, env=env, stdout=subprocess.PIPE,
+                       stderr=subprocess.PIPE, text=True, timeout=30)
+    assert r.returncode == 0, r.stderr
+    assert "MPI processes: 1" in r.stdout
+
+
+def test_cli_external_launcher_missing_peer_times_out_with_a_message(hooks, golden_dir, tmp_path):
+    """Opted in, but the peer never shows up: the barrier has a deadline, the job ends with a clear message and the
+    board of the launch is removed."""
+    fa = os.path.join(golden_dir, "ELSES_MATRIX_VCNT400std_A.mtx")
+    board = tmp_path / "board.bin"
+    env = dict(_clean_env(), EKB200_RENDEZVOUS=str(board), EKB200_RENDEZVOUS_TIMEOUT="2", RANK="0", WORLD_SIZE="2")
+    r = subprocess.run([APP, "-s", "b200", "--dry-run", fa], cwd=tmp_path, env=env, stdout=subprocess.PIPE,
+                       stderr=subprocess.PIPE, text=True, timeout=30)
+    assert r.returncode == 1
+    assert "rendezvous of 2 ranks timed out" in r.stderr
+    assert not board.exists()
+    # a rank > 0 whose rank 0 never creates the board gives up the same way
+    env["RANK"] = "1"
+    r = subprocess.run([APP, "-s", "b200", "--dry-run", fa], cwd=tmp_path, env=env, stdout=subprocess.PIPE,
+                       stderr=subprocess.PIPE, text=True, timeout=30)
+    assert r.returncode == 1 and "no board from rank 0" in r.stderr
+
+
+def test_cli_external_launcher_ignores_stale_board_and_symlinks(hooks, golden_dir, tmp_path):
+    """A crashed launch leaves id_ready = 1, an old NCCL id and a non-zero barrier count behind; a hostile user may plant
+    a symlink at the predictable name.  Rank 0 creates the board exclusively (O_EXCL | O_NOFOLLOW, stale files
+    unlinked), the other ranks only accept a board whose creator is alive."""
+    import struct
+
+    fa = os.path.join(golden_dir, "ELSES_MATRIX_VCNT400std_A.mtx")
+    board = tmp_path / "board.bin"
+    victim = tmp_path / "victim.txt"
+    victim.write_text("do not clobber")
+    for plant in ("stale", "symlink"):
+        if plant == "stale":  # magic ok, dead creator (pid 2^22 + 5 does not exist), id_ready = 1, barrier mid-way
+            board.write_bytes(struct.pack("<Iiiiii", 0x454B4232, 4194309, 2, 1, 7, 1) + b"\xff" * 200)
+        else:
+            os.symlink(victim, board)
+        procs = []
+        for r in (1, 0):  # rank 1 first: it must not latch onto the leftover
+            env = dict(_clean_env(), EKB200_RENDEZVOUS=str(board), EKB200_RENDEZVOUS_TIMEOUT="20", RANK=str(r),
+                       WORLD_SIZE="2")
+            procs.append(subprocess.Popen([APP, "-s", "b200", "--dry-run", fa], cwd=tmp_path, env=env,
+                                          stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+            if r == 1:
+                import time
+                time.sleep(0.3)
+        outs = [p.communicate(timeout=60) for p in procs]
+        assert [p.returncode for p in procs] == [0, 0], (plant, outs)
+        assert "MPI processes: 2" in outs[1][0]
+        assert not board.exists() and not os.path.islink(board)
+        assert victim.read_text() == "do not clobber"
+
+
 @pytest.mark.parametrize("args,code,needle", [
     (["-s", "nope", "A"], 1, "[Error] validate_argument: Unknown solver 'nope'"),
     (["-s", "b200", "A", "B"], 1, "[Error] validate_argument: solver 'b200' is not for generalized eigenvalue problem"),
