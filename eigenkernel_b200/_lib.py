@@ -94,6 +94,7 @@ _SIGS = {
     "ekb200_comm_init": [c_void_p, c_int, c_int, c_void_p],
     "ekb200_comm_info": [c_void_p, POINTER(c_int), POINTER(c_int)],
     "ekb200_comm_slab": [c_void_p, c_int64, POINTER(c_int64), POINTER(c_int64)],
+    "ekb200_comm_local_cols": [c_void_p, c_int64, POINTER(c_int64)],
     "ekb200_comm_allgather_slabs": [c_void_p, c_int64, c_int64, c_void_p, c_int64],
     "ekb200_comm_bcast": [c_void_p, c_void_p, c_int64, c_int],
     "ekb200_num_collectives": [c_void_p],

@@ -3,6 +3,8 @@
 
 #include <string.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 using namespace ekb;
@@ -136,6 +138,11 @@ int ekb200_set_option(ekb200_ctx* h, const char* key, int64_t value) {
   if (!strcmp(key, "sb2st_cps")) {  // cap on resident bulge-chasing CTAs per SM (tuning; 0 = no cap)
     if (value < 0 || value > 4) return -3;
     ctx->sb2st_cps = (int)value;
+    return 0;
+  }
+  if (!strcmp(key, "out_block")) {  // block size NB of the caller's 1 x P block-cyclic eigenvector descriptor (0: slabs)
+    if (value < 0) return -3;
+    ctx->out_block = value;
     return 0;
   }
   if (!strcmp(key, "q2_kc")) {
@@ -578,6 +585,11 @@ static int solve_host(ekb200_ctx* h, int64_t n, int64_t nev, const double* A, in
       rc = syevd_dev(ctx, n, nev, dA, ld, dw, dZ, ld, &h->merge_flops);
     }
   }
+  int warn = 0;
+  if (rc > EKB_WARN_STEIN && rc < EKB_FAIL_STEDC) {  // unconverged inverse iteration: a warning, the results are complete
+    warn = rc;
+    rc = 0;
+  }
   if (!rc) {
     StageTimer t(ctx, hasB ? "solve_with_general_b200:d2h" : "eigen_solver_b200:d2h");
     // multi-rank: every rank returns all of w and ITS column slab of the eigenvectors; the caller's Z is then
@@ -586,8 +598,21 @@ static int solve_host(ekb200_ctx* h, int64_t n, int64_t nev, const double* A, in
     slab_bounds(nev, ctx->nranks, 128, zb);
     const i64 c0 = zb[ctx->rank], kc = zb[ctx->rank + 1] - zb[ctx->rank];
     cudaError_t ce = cudaMemcpyAsync(w, dw, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream);
-    if (ce == cudaSuccess && kc > 0)
+    if (ctx->nranks > 1 && ctx->out_block > 0) {
+      // the caller's descriptor is block-cyclic with block size out_block (layout.h): every rank gets all columns over
+      // NVLink (one all-gather of the slabs), then copies out the blocks r, r + P, ... it owns
+      int rc2 = ce == cudaSuccess ? comm_allgather_cols(ctx, dZ, ld, zb) : 0;
+      if (rc2) { t.stop(); cleanup(); return rc2; }
+      const i64 nb = ctx->out_block;
+      const i64 nloc = numroc0(nev, nb, ctx->rank, ctx->nranks);
+      for (i64 lc = 0; lc < nloc && ce == cudaSuccess; lc += nb) {
+        const i64 g = cyclic_global_col0(lc, nb, ctx->nranks, ctx->rank);
+        const i64 wdt = std::min(nb, nloc - lc);
+        ce = cudaMemcpy2DAsync(Z + lc * ldz, ldz * 8, dZ + g * ld, ld * 8, n * 8, wdt, cudaMemcpyDeviceToHost, ctx->stream);
+      }
+    } else if (ce == cudaSuccess && kc > 0) {
       ce = cudaMemcpy2DAsync(Z, ldz * 8, dZ + c0 * ld, ld * 8, n * 8, kc, cudaMemcpyDeviceToHost, ctx->stream);
+    }
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
     t.stop();
     if (ce != cudaSuccess) {
@@ -597,7 +622,7 @@ static int solve_host(ekb200_ctx* h, int64_t n, int64_t nev, const double* A, in
     }
   }
   cleanup();
-  return rc;
+  return rc ? rc : warn;
 }
 
 int ekb200_syevd(ekb200_ctx* h, int64_t n, int64_t nev, const double* A, int64_t lda, double* w, double* Z,
@@ -718,8 +743,18 @@ static int verify_host(ekb200_ctx* h, int what, int64_t n, int64_t nvec, int64_t
     slab_bounds(nvec, ctx->nranks, 128, zb);
     const i64 c0 = zb[ctx->rank], kc = zb[ctx->rank + 1] - zb[ctx->rank];
     cudaError_t ce = cudaSuccess;
-    if (kc > 0)
+    const bool cyclic = ctx->nranks > 1 && ctx->out_block > 0;  // X is the block-cyclic local piece (option "out_block")
+    if (cyclic) {
+      rc = set_zero(ctx, dX, ld, ld, nvec);
+      const i64 nb = ctx->out_block, nloc = numroc0(nvec, nb, ctx->rank, ctx->nranks);
+      for (i64 lc = 0; lc < nloc && ce == cudaSuccess && !rc; lc += nb) {
+        const i64 g = cyclic_global_col0(lc, nb, ctx->nranks, ctx->rank);
+        ce = cudaMemcpy2DAsync(dX + g * ld, ld * 8, X + lc * ldx, ldx * 8, n * 8, std::min(nb, nloc - lc),
+                               cudaMemcpyHostToDevice, ctx->stream);
+      }
+    } else if (kc > 0) {
       ce = cudaMemcpy2DAsync(dX + c0 * ld, ld * 8, X, ldx * 8, n * 8, kc, cudaMemcpyHostToDevice, ctx->stream);
+    }
     if (ce == cudaSuccess && what == 0)
       ce = cudaMemcpyAsync(dw, w, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream);
     if (ce != cudaSuccess) {
@@ -728,7 +763,8 @@ static int verify_host(ekb200_ctx* h, int what, int64_t n, int64_t nvec, int64_t
       rc = EKB_ERR_CUDA;
     }
     // the checked columns need not coincide with the rank's slab of the nvec computed ones: make X whole
-    if (!rc && ctx->nranks > 1) rc = comm_allgather_cols(ctx, dX, ld, zb);
+    if (!rc && cyclic) rc = comm_allreduce_sum(ctx, dX, (size_t)ld * nvec);  // disjoint pieces: the sum is a gather
+    else if (!rc && ctx->nranks > 1) rc = comm_allgather_cols(ctx, dX, ld, zb);
   }
   if (!rc) {
     if (what == 0) rc = eval_residual_norm(ctx, n, a1, dA, ld, dB, ld, dw, dX, ld, o1, o2, o3);
@@ -807,6 +843,16 @@ int ekb200_comm_slab(const ekb200_ctx* h, int64_t ncols, int64_t* col0, int64_t*
   if (col0) *col0 = zb[h->c.rank];
   if (nloc) *nloc = zb[h->c.rank + 1] - zb[h->c.rank];
   return 0;
+}
+int ekb200_comm_local_cols(const ekb200_ctx* h, int64_t ncols, int64_t* nloc) {
+  if (!h) return -1;
+  if (ncols < 0) return -2;
+  if (!nloc) return -3;
+  if (h->c.nranks > 1 && h->c.out_block > 0) {
+    *nloc = numroc0(ncols, h->c.out_block, h->c.rank, h->c.nranks);
+    return 0;
+  }
+  return ekb200_comm_slab(h, ncols, nullptr, nloc);
 }
 int ekb200_comm_allgather_slabs(ekb200_ctx* h, int64_t nrows, int64_t ncols, double* M, int64_t ld) {
   CHECK_CTX(h);

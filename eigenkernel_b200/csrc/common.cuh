@@ -56,6 +56,7 @@ struct Ctx {
   int sb2st_warps = 8;                // compute warps per CTA of the register-resident kernel (8 | 16)
   int sb2st_rwarp = 1;                // 1: one extra warp forms the reflectors beside the updates; 0: warp 0 does
   int sb2st_cps = 0;                  // cap on resident CTAs per SM (0 = what the occupancy calculator allows)
+  long long out_block = 0;            // > 0: host entry points deliver the 1 x P block-cyclic piece with this block size (layout.h)
   int q2_kc = 0;                      // columns of Z per CTA in apply_q2 (0 = choose; 64|80|96|112|128)
   // stage timers
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;

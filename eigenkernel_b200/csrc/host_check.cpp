@@ -32,6 +32,17 @@ extern "C" int ekb200_host_slab_bounds(long long ncols, int nranks, int gran, lo
   return 0;
 }
 
+// the caller-side block-cyclic view of the eigenvector matrix (option "out_block"): clamp, numroc, local -> global column
+extern "C" long long ekb200_host_block_clamp(long long rows, long long cols, long long want, int nprow, int npcol) {
+  return ekb::reference_block_clamp(rows, cols, want, nprow, npcol);
+}
+extern "C" long long ekb200_host_numroc(long long n, long long nb, int iproc, int nprocs) {
+  return ekb::numroc0(n, nb, iproc, nprocs);
+}
+extern "C" long long ekb200_host_cyclic_global_col(long long lc, long long nb, int nprocs, int r) {
+  return ekb::cyclic_global_col0(lc, nb, nprocs, r);
+}
+
 // ---- bisection + inverse iteration (tridiag.cuh), the host run of exactly the code the CUDA kernels execute
 static void tri_setup(long long n, const double* d, const double* e, std::vector<double>& e2, double* gl, double* gu,
                       double* onenrm, double* pivmin) {

@@ -19,6 +19,32 @@ inline void slab_bounds(long long ncols, int nranks, int gran, std::vector<long 
   }
 }
 
+// ---- the caller's ScaLAPACK view of the result (rank-per-GPU Fortran mode).  setup_distributed_matrix
+// (reference src/distribute_matrix.f90:92-148) allocates blacs%Vectors for a block-cyclic descriptor whose block size it
+// CLAMPS to max(min(rows / nprow, cols / npcol), 1) (:114-120) "so that no process is empty"; on the 1 x P grid of the B200
+// solvers that is floor(ncols / P), which differs from the library's own slab width (ceil(ncols / P) rounded up to 128)
+// unless 128 P divides ncols.  With option "out_block" = NB the host-pointer entry points therefore deliver each rank's
+// piece of the 1 x P block-cyclic distribution with block size NB (numroc columns; blocks r, r + P, ... of rank r).
+inline long long reference_block_clamp(long long rows, long long cols, long long want, int nprow, int npcol) {
+  long long a = rows / nprow, b = cols / npcol;
+  long long mx = a < b ? a : b;
+  if (mx < 1) mx = 1;
+  return want > mx ? mx : want;
+}
+// ScaLAPACK NUMROC(n, nb, iproc, isrcproc = 0, nprocs)
+inline long long numroc0(long long n, long long nb, int iproc, int nprocs) {
+  const long long nblocks = n / nb;
+  long long loc = (nblocks / nprocs) * nb;
+  const long long extra = nblocks % nprocs;
+  if (iproc < extra) loc += nb;
+  else if (iproc == extra) loc += n % nb;
+  return loc;
+}
+// global column of local column lc of rank r (block size nb, P ranks, source rank 0)
+inline long long cyclic_global_col0(long long lc, long long nb, int nprocs, int r) {
+  return ((lc / nb) * nprocs + r) * nb + lc % nb;
+}
+
 // Block-column-cyclic ownership used by the sharded dense-to-band reduction: block column c (width cb) of the
 // matrix belongs to rank c mod P.
 inline int block_owner(long long block, int nranks) { return (int)(block % nranks); }

@@ -259,19 +259,53 @@ __device__ __forceinline__ int ld_poll_gpu(const int* p) {
   asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+// Wait until *p >= need.  One poll costs an L2 round trip (~1 us here), so a single load in flight notices a
+// change half a round trip late on average; four loads kept in flight, a quarter of a round trip apart, cut that to
+// an eighth.  (The counter only grows, any observed value >= need is final.)
+__device__ __forceinline__ void wait_progress(const int* p, int need) {
+  int v0 = ld_poll_gpu(p);
+  if (v0 >= need) return;
+  const long long t0 = clock64();
+  int v1 = ld_poll_gpu(p);
+  while (clock64() - t0 < 250) {}
+  int v2 = ld_poll_gpu(p);
+  while (clock64() - t0 < 500) {}
+  int v3 = ld_poll_gpu(p);
+  for (;;) {
+    if (v1 >= need) return;
+    v1 = ld_poll_gpu(p);
+    if (v2 >= need) return;
+    v2 = ld_poll_gpu(p);
+    if (v3 >= need) return;
+    v3 = ld_poll_gpu(p);
+    v0 = ld_poll_gpu(p);
+    if (v0 >= need) return;
+  }
+}
+__device__ __forceinline__ double ldcg_f64(const double* p) {
+  double v;
+  asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
 __device__ __forceinline__ void st_release_gpu(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ double shx(double x, int m) { return __shfl_xor_sync(0xffffffffu, x, m); }
 __device__ __forceinline__ double shi(double x, int src) { return __shfl_sync(0xffffffffu, x, src); }
 
-// y[c] <- sum over the 32 lanes of y[c], for all c, in every lane (bit-identical in all lanes): reduce-scatter by a
-// transposed butterfly (CW/2 + CW/4 + .. exchanges), plain butterfly on the one remaining value, all-gather.
+// Column sums over the 32 lanes by a transposed butterfly (reduce-scatter: CW/2 + CW/4 + .. exchanges, then a plain
+// butterfly on the one remaining value).  Returns the total of column warp_col_of_lane<CW>(lane); the 32 / CW lanes that
+// share a column hold bit-identical values.
 template <int CW>
-__device__ __forceinline__ void warp_allreduce_cols(double (&y)[CW], int lane) {
+__device__ __forceinline__ int warp_col_of_lane(int lane) {
+  return CW == 8 ? (lane >> 2) : (lane >> 3);
+}
+template <int CW>
+__device__ __forceinline__ double warp_reduce_cols(const double (&y)[CW], int lane) {
   static_assert(CW == 8 || CW == 4, "columns per warp");
+  double c1;
   if constexpr (CW == 8) {
-    double a[4], b2[2], c1;
+    double a[4], b2[2];
     const bool h4 = lane & 16, h3 = lane & 8, h2 = lane & 4;
 #pragma unroll
     for (int k = 0; k < 4; ++k) a[k] = (h4 ? y[k + 4] : y[k]) + shx(h4 ? y[k] : y[k + 4], 16);
@@ -279,23 +313,32 @@ __device__ __forceinline__ void warp_allreduce_cols(double (&y)[CW], int lane) {
     for (int k = 0; k < 2; ++k) b2[k] = (h3 ? a[k + 2] : a[k]) + shx(h3 ? a[k] : a[k + 2], 8);
     c1 = (h2 ? b2[1] : b2[0]) + shx(h2 ? b2[0] : b2[1], 4);
     c1 += shx(c1, 2);
-    c1 += shx(c1, 1);
-    // this lane now holds the total of column 4 bit4 + 2 bit3 + bit2
-#pragma unroll
-    for (int k = 0; k < 8; ++k) y[k] = shi(c1, ((k >> 2) & 1) * 16 + ((k >> 1) & 1) * 8 + (k & 1) * 4);
+    c1 += shx(c1, 1);  // column 4 bit4 + 2 bit3 + bit2 = lane >> 2
   } else {
-    double a[2], c1;
+    double a[2];
     const bool h4 = lane & 16, h3 = lane & 8;
 #pragma unroll
     for (int k = 0; k < 2; ++k) a[k] = (h4 ? y[k + 2] : y[k]) + shx(h4 ? y[k] : y[k + 2], 16);
     c1 = (h3 ? a[1] : a[0]) + shx(h3 ? a[0] : a[1], 8);
     c1 += shx(c1, 4);
     c1 += shx(c1, 2);
-    c1 += shx(c1, 1);
-    // this lane now holds the total of column 2 bit4 + bit3
-#pragma unroll
-    for (int k = 0; k < 4; ++k) y[k] = shi(c1, ((k >> 1) & 1) * 16 + (k & 1) * 8);
+    c1 += shx(c1, 1);  // column 2 bit4 + bit3 = lane >> 3
   }
+  return c1;
+}
+
+// sum of NW values p[0], p[stride], ... as a balanced tree (depth log2 NW instead of NW dependent additions); every
+// caller uses this one order, so the redundant copies of u and p in the different warps are bit-identical
+template <int NW>
+__device__ __forceinline__ double tree_sum(const double* p, int stride) {
+  double t[NW];
+#pragma unroll
+  for (int w = 0; w < NW; ++w) t[w] = p[w * stride];
+#pragma unroll
+  for (int m = NW / 2; m >= 1; m >>= 1)
+#pragma unroll
+    for (int w = 0; w < m; ++w) t[w] += t[w + m];
+  return t[0];
 }
 
 __device__ __forceinline__ double warp_allreduce_sum(double x) {
@@ -354,10 +397,16 @@ sb2st_reg_kernel(double* __restrict__ AB, i64 ldab, i64 n, double* __restrict__ 
   __shared__ double s_pu[NW][B];
   __shared__ double s_pp[NW][B];
   __shared__ double s_pc[B];
+  __shared__ __align__(16) double s_y[NW][CW];  // column dots of the L block, per warp
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool compute = warp < NW;
   const int j0 = warp * CW;
-  const i64 cstep = ldab - 1;  // one column to the right along a matrix row, in band storage
+  // The band is stored with exactly 2 B rows (what the solver allocates; the host falls back to the round-1 kernel
+  // otherwise): every band offset below is then an immediate, which removes most of the integer arithmetic of a task
+  // -- and the per-warp instruction count IS the task time here (about 2 warps per scheduler, dependent chains).
+  constexpr i64 LDAB = 2 * B;
+  constexpr i64 cstep = LDAB - 1;  // one column to the right along a matrix row, in band storage
+  (void)ldab;
   int trace_task = 0;
   auto stamp = [&](int k, int slot) {
     if constexpr (TRACE) {
@@ -373,7 +422,7 @@ sb2st_reg_kernel(double* __restrict__ AB, i64 ldab, i64 n, double* __restrict__ 
     // ---- prologue: reflector of task 0 from column s (needs task 0 of sweep s-1, look-ahead included)
     if (warp == RWARP) {
       if (s > 0) {
-        if (lane == 0) while (ld_poll_gpu(prog + (s - 1)) < 1) {}
+        if (lane == 0) wait_progress(prog + (s - 1), 1);
         __syncwarp();
       }
       const i64 r0 = s + 1;
@@ -382,7 +431,7 @@ sb2st_reg_kernel(double* __restrict__ AB, i64 ldab, i64 n, double* __restrict__ 
 #pragma unroll
       for (int h = 0; h < RH; ++h) {
         const int row = lane + 32 * h;
-        x[h] = row < nr ? __ldcg(AB + s * ldab + 1 + row) : 0.0;
+        x[h] = row < nr ? __ldcg(AB + s * LDAB + 1 + row) : 0.0;
       }
       warp_reflector<RH>(x, nr, lane, v, tau, beta);
 #pragma unroll
@@ -391,7 +440,7 @@ sb2st_reg_kernel(double* __restrict__ AB, i64 ldab, i64 n, double* __restrict__ 
         s_v[0][row] = v[h];
         if (row < nr) {
           V2[s * ldv + r0 + row] = v[h];
-          AB[s * ldab + 1 + row] = (row == 0) ? beta : 0.0;
+          AB[s * LDAB + 1 + row] = (row == 0) ? beta : 0.0;
         }
       }
       if (lane == 0) {
@@ -399,17 +448,45 @@ sb2st_reg_kernel(double* __restrict__ AB, i64 ldab, i64 n, double* __restrict__ 
         TAU2[s * (i64)ldtau] = tau;
       }
     }
-    double Bt[RH][CW];
+    double Bt[RH][CW], Dt[RH][CW];
 #pragma unroll
     for (int h = 0; h < RH; ++h)
 #pragma unroll
-      for (int c = 0; c < CW; ++c) Bt[h][c] = 0.0;
+      for (int c = 0; c < CW; ++c) Bt[h][c] = Dt[h][c] = 0.0;
+    double* dprev = nullptr;  // D block of the previous task: updated in registers, all columns but the first not yet stored
+    int nrprev = 0;
+    // D_t goes to the band in two parts.  Column 0 (and the beta of the look-ahead) is all that the task which waits
+    // for THIS task's completion reads of it; it is stored at once.  The other columns are only read one task later,
+    // i.e. under the NEXT completion count, so they are stored after this task's count has been published: the
+    // release then has no fresh stores to wait for (it used to sit behind 16 KB written a few hundred clocks before).
+    auto store_deferred_D = [&]() {
+      if (dprev == nullptr) return;
+      if (nrprev == B) {
+#pragma unroll
+        for (int c = 0; c < CW; ++c)
+#pragma unroll
+          for (int h = 0; h < RH; ++h) {
+            const int row = lane + 32 * h, col = j0 + c;
+            if (col > 0 && row >= col) dprev[c * cstep + 32 * h] = Dt[h][c];
+          }
+      } else {
+#pragma unroll
+        for (int c = 0; c < CW; ++c)
+#pragma unroll
+          for (int h = 0; h < RH; ++h) {
+            const int row = lane + 32 * h, col = j0 + c;
+            if (col > 0 && col < nrprev && row >= col && row < nrprev) dprev[c * cstep + 32 * h] = Dt[h][c];
+          }
+      }
+      dprev = nullptr;
+    };
 
     for (int t = 0; t < ntask; ++t) {
       const int cur = t & 1;
       __syncthreads();  // v_t, tau_t visible; every store of task t-1 has been issued
       if (tid == 0 && t > 0) st_release_gpu(prog + s, t);  // tasks 0 .. t-1 complete (and beta_t is in the band)
       if (traced) stamp(0, tslot);
+      if (compute) store_deferred_D();
       const double tau = s_tau[cur];
       const i64 r0 = s + 1 + (i64)t * B;
       const int nr = (int)min((i64)B, n - r0);                             // rows of R (>= 2)
@@ -434,39 +511,79 @@ sb2st_reg_kernel(double* __restrict__ AB, i64 ldab, i64 n, double* __restrict__ 
 #pragma unroll
             for (int h = 0; h < RH; ++h) y[c] = fma(vr[h], Bt[h][c], y[c]);
           }
-          warp_allreduce_cols<CW>(y, lane);
+          {
+            const double tot = tau * warp_reduce_cols<CW>(y, lane);
+            if ((lane & (32 / CW - 1)) == 0) s_y[warp][warp_col_of_lane<CW>(lane)] = tot;
+            __syncwarp();
 #pragma unroll
-          for (int c = 0; c < CW; ++c) y[c] *= tau;
-          if (warp == 0) y[0] = 0.0;  // column 0 already is beta e1
-          double* lp = AB + (r0 - B + j0) * ldab + (B - j0) + lane;  // element (row = lane, col = j0)
-#pragma unroll
-          for (int c = 0; c < CW; ++c)
-#pragma unroll
-            for (int h = 0; h < RH; ++h) {
-              const int row = lane + 32 * h;
-              Bt[h][c] = fma(-vr[h], y[c], Bt[h][c]);
-              // (0,0) = beta went to the band with the look-ahead; a later sweep may already have overwritten it
-              if (row < nr && !(warp == 0 && c == 0 && row == 0)) lp[c * cstep + 32 * h] = Bt[h][c];
+            for (int c = 0; c < CW; c += 2) {
+              const double2 t2 = *reinterpret_cast<const double2*>(&s_y[warp][c]);
+              y[c] = t2.x;
+              y[c + 1] = t2.y;
             }
+            __syncwarp();  // s_y[warp] is rewritten by this warp in the next task
+          }
+          if (warp == 0) y[0] = 0.0;  // column 0 already is beta e1
+          double* lp = AB + (r0 - B + j0) * LDAB + (B - j0) + lane;  // element (row = lane, col = j0)
+          if (nr == B) {  // full block: unpredicated stores (all but the one element of the look-ahead)
+#pragma unroll
+            for (int c = 0; c < CW; ++c)
+#pragma unroll
+              for (int h = 0; h < RH; ++h) {
+                Bt[h][c] = fma(-vr[h], y[c], Bt[h][c]);
+                if (c == 0 && h == 0) {
+                  if (tid != 0) lp[0] = Bt[0][0];
+                } else {
+                  lp[c * cstep + 32 * h] = Bt[h][c];
+                }
+              }
+          } else {
+#pragma unroll
+            for (int c = 0; c < CW; ++c)
+#pragma unroll
+              for (int h = 0; h < RH; ++h) {
+                const int row = lane + 32 * h;
+                Bt[h][c] = fma(-vr[h], y[c], Bt[h][c]);
+                // (0,0) = beta went to the band with the look-ahead; a later sweep may already have overwritten it
+                if (row < nr && !(warp == 0 && c == 0 && row == 0)) lp[c * cstep + 32 * h] = Bt[h][c];
+              }
+          }
         }
         if (traced) stamp(1, tslot);
         // ---- wait for sweep s-1: tasks 0 .. t+1 complete
         if (s > 0) {
-          if (lane == 0) while (ld_poll_gpu(prog + (s - 1)) < t + 2) {}
+          if (lane == 0) wait_progress(prog + (s - 1), t + 2);
           __syncwarp();
         }
         if (traced) stamp(2, tslot);
         // ---- D block (lower triangle of A(R,R)) and B block (A(R+B, R))
-        double Dt[RH][CW];
-        double* dp = AB + (r0 + j0) * ldab - j0 + lane;  // D element (row = lane, col = j0); B element: B rows below
+        double* dp = AB + (r0 + j0) * LDAB - j0 + lane;  // D element (row = lane, col = j0); B element: B rows below
+        if (nr == B && nr2 == B) {
+          // interior task (all but the last two of a sweep): 2 RH CW unconditional loads issued back to back -- ONE
+          // L2 round trip; the part of D above the diagonal reads the tail of the neighbouring band column (valid
+          // memory) and is zeroed afterwards
 #pragma unroll
-        for (int c = 0; c < CW; ++c)
+          for (int c = 0; c < CW; ++c)
 #pragma unroll
-          for (int h = 0; h < RH; ++h) {
-            const int row = lane + 32 * h, col = j0 + c;
-            Dt[h][c] = (col < nr && row >= col && row < nr) ? __ldcg(dp + c * cstep + 32 * h) : 0.0;
-            Bt[h][c] = (col < nr && row < nr2) ? __ldcg(dp + c * cstep + 32 * h + B) : 0.0;
-          }
+            for (int h = 0; h < RH; ++h) {
+              Dt[h][c] = ldcg_f64(dp + c * cstep + 32 * h);
+              Bt[h][c] = ldcg_f64(dp + c * cstep + 32 * h + B);
+            }
+#pragma unroll
+          for (int c = 0; c < CW; ++c)
+#pragma unroll
+            for (int h = 0; h < RH; ++h)
+              if (lane + 32 * h < j0 + c) Dt[h][c] = 0.0;
+        } else {
+#pragma unroll
+          for (int c = 0; c < CW; ++c)
+#pragma unroll
+            for (int h = 0; h < RH; ++h) {
+              const int row = lane + 32 * h, col = j0 + c;
+              Dt[h][c] = (col < nr && row >= col && row < nr) ? __ldcg(dp + c * cstep + 32 * h) : 0.0;
+              Bt[h][c] = (col < nr && row < nr2) ? __ldcg(dp + c * cstep + 32 * h + B) : 0.0;
+            }
+        }
         // ---- partial dots: u = tau B v (rows), p = tau D v (rows from the lower triangle, columns from its transpose)
         {
           double pu[RH], pp[RH], pcq[CW];
@@ -491,16 +608,14 @@ sb2st_reg_kernel(double* __restrict__ AB, i64 ldab, i64 n, double* __restrict__ 
             if (pu[0] + pp[0] + pcq[0] == 1.2345e300) trace[0] = 0;  // consume the loads before the stamp
             if (traced) stamp(3, tslot);
           }
-          warp_allreduce_cols<CW>(pcq, lane);
 #pragma unroll
           for (int h = 0; h < RH; ++h) {
             s_pu[warp][lane + 32 * h] = pu[h];
             s_pp[warp][lane + 32 * h] = pp[h];
             if (RW && warp == 0) s_x[lane + 32 * h] = Bt[h][0];
           }
-#pragma unroll
-          for (int c = 0; c < CW; ++c)
-            if (lane == c) s_pc[j0 + c] = pcq[c];
+          const double ctot = warp_reduce_cols<CW>(pcq, lane);
+          if ((lane & (32 / CW - 1)) == 0) s_pc[j0 + warp_col_of_lane<CW>(lane)] = ctot;
         }
         if (traced) stamp(4, tslot);
         __syncthreads();
@@ -514,14 +629,8 @@ sb2st_reg_kernel(double* __restrict__ AB, i64 ldab, i64 n, double* __restrict__ 
 #pragma unroll
           for (int h = 0; h < RH; ++h) {
             const int row = lane + 32 * h;
-            double a = 0.0, q = 0.0;
-#pragma unroll
-            for (int w = 0; w < NW; ++w) {
-              a += s_pu[w][row];
-              q += s_pp[w][row];
-            }
-            u[h] = tau * a;
-            pv[h] = tau * (q + s_pc[row]);
+            u[h] = tau * tree_sum<NW>(&s_pu[0][row], B);
+            pv[h] = tau * (tree_sum<NW>(&s_pp[0][row], B) + s_pc[row]);
             sig = fma(pv[h], vr[h], sig);
           }
           sig = warp_allreduce_sum(sig);
@@ -541,9 +650,12 @@ sb2st_reg_kernel(double* __restrict__ AB, i64 ldab, i64 n, double* __restrict__ 
             const int row = lane + 32 * h, col = j0 + c;
             double dv = fma(-vr[h], wc[c], Dt[h][c]);
             dv = fma(-wv[h], vc[c], dv);
-            if (col < nr && row >= col && row < nr) dp[c * cstep + 32 * h] = dv;
+            Dt[h][c] = dv;
+            if (col == 0 && row < nr) dp[32 * h] = dv;  // column 0 now, the rest after the completion count
             Bt[h][c] = fma(-u[h], vc[c], Bt[h][c]);
           }
+        dprev = dp;
+        nrprev = nr;
         if (traced) stamp(6, tslot);
         if (last) {
 #pragma unroll
@@ -565,9 +677,7 @@ sb2st_reg_kernel(double* __restrict__ AB, i64 ldab, i64 n, double* __restrict__ 
 #pragma unroll
           for (int h = 0; h < RH; ++h) {
             const int row = lane + 32 * h;
-            double a = 0.0;
-#pragma unroll
-            for (int w = 0; w < NW; ++w) a += s_pu[w][row];
+            const double a = tree_sum<NW>(&s_pu[0][row], B);
             x[h] = fma(-(tau * a), v0, s_x[row]);  // the same expression the compute warps apply to column 0
           }
         } else {
@@ -586,12 +696,13 @@ sb2st_reg_kernel(double* __restrict__ AB, i64 ldab, i64 n, double* __restrict__ 
           s_tau[cur ^ 1] = taun;
           s_beta[cur ^ 1] = betan;
           TAU2[s * (i64)ldtau + t + 1] = taun;
-          AB[r0 * ldab + B] = betan;
+          AB[r0 * LDAB + B] = betan;
         }
         stamp(7, 0);
       }
       if constexpr (TRACE) ++trace_task;
     }
+    if (compute) store_deferred_D();
     __syncthreads();
     if (tid == 0) st_release_gpu(prog + s, DONE);
   }
@@ -649,7 +760,7 @@ static int sb2st_reg_dispatch(Ctx* ctx, i64 n, int b, double* AB, i64 ldab, doub
 int sb2st(Ctx* ctx, i64 n, int b, double* AB, i64 ldab, double* V2, i64 ldv, double* TAU2, int ldtau, int* prog,
           double* d, double* e) {
   if (n <= 0) return 0;
-  if (n >= 3 && ctx->sb2st_variant != 0) {
+  if (n >= 3 && ctx->sb2st_variant != 0 && ldab == 2 * (i64)b) {
     EKB_CUDA(cudaMemsetAsync(prog, 0, (size_t)n * sizeof(int), ctx->stream));
     EKB_TRY(prof_begin(ctx, PROF_SB2ST, 12.0 * b * (double)n * (double)n));  // effective bytes, SURVEY 8(d)
     int rc;

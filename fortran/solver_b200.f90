@@ -77,6 +77,12 @@ module ek_solver_b200_m
       integer(c_int64_t), value :: ncols
       integer(c_int64_t), intent(out) :: col0, nloc
     end function ekb200_comm_slab
+    integer(c_int) function ekb200_comm_local_cols(ctx, ncols, nloc) bind(C, name='ekb200_comm_local_cols')
+      import :: c_ptr, c_int, c_int64_t
+      type(c_ptr), value :: ctx
+      integer(c_int64_t), value :: ncols
+      integer(c_int64_t), intent(out) :: nloc
+    end function ekb200_comm_local_cols
     integer(c_int) function ekb200_num_events(ctx) bind(C, name='ekb200_num_events')
       import :: c_ptr, c_int
       type(c_ptr), value :: ctx
@@ -150,6 +156,7 @@ contains
     real(c_double), allocatable :: v_dummy(:)
     character(kind=c_char) :: nccl_id(128)
     integer :: ierr
+    integer, external :: numroc   ! ScaLAPACK TOOLS (the reference uses it the same way, distribute_matrix.f90:84-88)
 
     if (proc%n_procs_row /= 1) then
       call terminate('solver_b200: the process grid must be 1 x P (one process column per B200)', 1)
@@ -177,13 +184,25 @@ contains
 
     eigenpairs%type_number = 2
     allocate(eigenpairs%blacs%values(n))
-    ! n x n_vec eigenvectors on the 1 x P grid, ONE block column per rank: block size = slab width of rank 0 (the
-    ! widest); on one rank this is the plain n x n_vec local array.  Consumers call blacs_gridinfo on desc(context_).
+    ! n x n_vec eigenvectors on the 1 x P grid.  The array and its descriptor come from the reference's own
+    ! setup_distributed_matrix, which CLAMPS the requested block size to max(min(rows/nprow, cols/npcol), 1)
+    ! (distribute_matrix.f90:114-120) -- e.g. n_vec = 6554 on 8 ranks gives NB = 819, not the library's slab width 896.
+    ! So ask for the slab width, then READ BACK the NB the descriptor really has and tell the library to deliver the
+    ! local piece of exactly that block-cyclic distribution (option "out_block"; numroc columns per rank, checked below).
+    ! On one rank this is the plain n x n_vec local array.  Consumers call blacs_gridinfo on desc(context_).
     info = ekb200_comm_slab(ctx, int(n_vec, c_int64_t), col0, nloc)
     slab_width = nloc
     call mpi_bcast(slab_width, 1, mpi_integer8, 0, mpi_comm_world, ierr)
     call setup_distributed_matrix('Eigenvectors', proc, n, n_vec, &
          eigenpairs%blacs%desc, eigenpairs%blacs%Vectors, block_size = int(max(slab_width, 1_c_int64_t)))
+    if (proc%n_procs > 1) then
+      info = ekb200_set_option(ctx, c_char_'out_block' // c_null_char, int(eigenpairs%blacs%desc(nb_), c_int64_t))
+      if (info /= 0) call terminate('solver_b200: option out_block rejected', info)
+      info = ekb200_comm_local_cols(ctx, int(n_vec, c_int64_t), nloc)
+      if (nloc /= numroc(n_vec, eigenpairs%blacs%desc(nb_), proc%my_proc_col, 0, proc%n_procs_col)) then
+        call terminate('solver_b200: library and descriptor disagree on the local column count', 1)
+      end if
+    end if
 
     if (present(matrix_B)) then
       info = ekb200_sygvd_coo(ctx, int(n, c_int64_t), int(n_vec, c_int64_t), &

@@ -40,7 +40,11 @@ int ekb200_set_option(ekb200_ctx* ctx, const char* key, int64_t value); /* "band
                                                                            "select_method" = 0 auto | 1 D&C | 2 bisection + inverse
                                                                            iteration for the -n solvers;
                                                                            "reduction" = 0 blocked pdsygst-style | 1 explicit inverse of
-                                                                           L (-s general_b200inv; solver_elpa_eigenexa.f90:110-150) */
+                                                                           L (-s general_b200inv; solver_elpa_eigenexa.f90:110-150);
+                                                                           "out_block" = NB of the caller's block-cyclic eigenvector
+                                                                           descriptor (see ekb200_comm_local_cols; 0 = column slabs);
+                                                                           tuning: "sb2st_variant", "sb2st_warps", "sb2st_rwarp",
+                                                                           "sb2st_cps", "q2_kc" */
 int ekb200_version(void);
 int ekb200_device_count(void); /* visible CUDA devices (0 when there is none); a rank uses device = local rank */
 
@@ -229,6 +233,14 @@ int ekb200_comm_unique_id(void* id128);
 int ekb200_comm_init(ekb200_ctx* ctx, int nranks, int rank, const void* id128);
 int ekb200_comm_info(const ekb200_ctx* ctx, int* nranks, int* rank);
 int ekb200_comm_slab(const ekb200_ctx* ctx, int64_t ncols, int64_t* col0, int64_t* nloc);
+/* Rank-per-GPU callers whose eigenvector array was allocated by setup_distributed_matrix (distribute_matrix.f90:92-148):
+ * that routine CLAMPS the block size to max(min(rows / nprow, cols / npcol), 1) (:114-120), i.e. floor(ncols / P) on
+ * the 1 x P grid, which is not the slab width above unless 128 P divides ncols.  Option "out_block" = NB (the NB of
+ * the caller's descriptor, desc(6)) makes the host-pointer entry points (ekb200_syevd / sygvd / sygvd_coo and the
+ * ekb200_eval_* / ekb200_get_ipratios host variants) exchange the LOCAL PIECE OF THAT 1 x P BLOCK-CYCLIC DISTRIBUTION:
+ * numroc(ncols, NB, rank, 0, P) columns, blocks rank, rank + P, ... (one NVLink all-gather inside the library).
+ * ekb200_comm_local_cols returns that column count (the slab width when "out_block" is 0). */
+int ekb200_comm_local_cols(const ekb200_ctx* ctx, int64_t ncols, int64_t* nloc);
 /* every rank owns its slab of the columns of dev_M (nrows x ncols, ld): afterwards all ranks hold all columns */
 int ekb200_comm_allgather_slabs(ekb200_ctx* ctx, int64_t nrows, int64_t ncols, double* dev_M, int64_t ld);
 int ekb200_comm_bcast(ekb200_ctx* ctx, void* dev_buf, int64_t bytes, int root);

@@ -105,6 +105,26 @@ def main():
         assert np.array_equal(wl, w), "host and device entry points disagree on eigenvalues"
         if kc > 0:
             assert np.array_equal(Xl[:, :kc], X[:, c0:c0 + kc]), "local piece != slab of the device result"
+        # the caller's ScaLAPACK view (rank-per-GPU Fortran mode): with option "out_block" = the NB that the reference's
+        # setup_distributed_matrix ends up with (clamped to floor(nev / P), distribute_matrix.f90:114-120) the host entry
+        # point delivers the numroc columns of that 1 x P block-cyclic descriptor: blocks rank, rank + P, ...
+        nb = max(min(n, nev // world), 1)
+        nb = min(nb, max(ekdist.slab_bounds(nev, world)[1], 1))
+        ctx.set_option("out_block", nb)
+        nl = ctypes.c_int64()
+        ctx.lib.ekb200_comm_local_cols(ctx.h, nev, ctypes.byref(nl))
+        nblk = nev // nb
+        want = (nblk // world) * nb + (nb if rank < nblk % world else (nev % nb if rank == nblk % world else 0))
+        assert nl.value == want, (nl.value, want)
+        wc, Xc = np.zeros(n), np.zeros((n, max(nl.value, 1)), order="F")
+        if gen:
+            info = ctx.call("ekb200_sygvd", n, nev, A.ctypes.data, n, B.ctypes.data, n, wc.ctypes.data, Xc.ctypes.data, n)
+        else:
+            info = ctx.call("ekb200_syevd", n, nev, A.ctypes.data, n, wc.ctypes.data, Xc.ctypes.data, n)
+        assert info == 0 and np.array_equal(wc, w)
+        gcols = [((lc // nb) * world + rank) * nb + lc % nb for lc in range(nl.value)]
+        assert np.array_equal(Xc[:, :nl.value], X[:, gcols]), "block-cyclic local piece != columns of the device result"
+        ctx.set_option("out_block", 0)
         # device-side checks through the host entry points: replicated COO in, local piece of X in (perturbed, so
         # that the metrics are well above rounding noise and can be compared tightly)
         Xl = np.asfortranarray(Xl + 1e-9 * np.random.default_rng(1000 + rank).standard_normal(Xl.shape))

@@ -70,3 +70,46 @@ def test_gloo_world2_plumbing(tmp_path):
     env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
     r = subprocess.run(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
     assert r.returncode == 0 and "HOST_DIST_OK" in r.stdout, r.stdout[-3000:]
+
+
+# ---- the caller's block-cyclic view of the eigenvectors (option "out_block", rank-per-GPU Fortran mode)
+def _numroc_ref(n, nb, iproc, isrc, nprocs):
+    """ScaLAPACK TOOLS/numroc.f, restated line by line."""
+    mydist = (nprocs + iproc - isrc) % nprocs
+    nblocks = n // nb
+    out = (nblocks // nprocs) * nb
+    extra = nblocks % nprocs
+    if mydist < extra:
+        out += nb
+    elif mydist == extra:
+        out += n % nb
+    return out
+
+
+@pytest.mark.parametrize("n,n_vec,P", [(30, 30, 2), (400, 400, 4), (65536, 6554, 8), (32768, 32768, 8), (1000, 7, 8),
+                                       (3000, 700, 4), (2000, 1999, 2)])
+def test_out_block_layout_matches_setup_distributed_matrix(n, n_vec, P):
+    """fortran/solver_b200.f90 allocates blacs%Vectors with the reference's setup_distributed_matrix, which clamps the
+    block size to max(min(rows/nprow, cols/npcol), 1) (distribute_matrix.f90:114-120); the library must deliver exactly
+    the numroc columns of THAT descriptor (blocks r, r + P, ...), not its own 128-granular slabs: (30, 2) gives NB 15
+    (slab 128), (6554, 8) gives 819 (slab 896)."""
+    import ctypes
+
+    lib = ctypes.CDLL(HC)
+    for f in (lib.ekb200_host_block_clamp, lib.ekb200_host_numroc, lib.ekb200_host_cyclic_global_col):
+        f.restype = ctypes.c_longlong
+    LL = ctypes.c_longlong
+    slab = ekdist.slab_bounds(n_vec, P)[1]                          # what the glue asks setup_distributed_matrix for
+    nb = lib.ekb200_host_block_clamp(LL(n), LL(n_vec), LL(max(slab, 1)), 1, P)
+    assert nb == min(max(slab, 1), max(min(n, n_vec // P), 1))
+    assert {(30, 2): 15, (400, 4): 100, (6554, 8): 819, (32768, 8): 4096}.get((n_vec, P), nb) == nb
+    owned = []
+    for r in range(P):
+        nloc = lib.ekb200_host_numroc(LL(n_vec), LL(nb), r, P)
+        assert nloc == _numroc_ref(n_vec, nb, r, 0, P)
+        cols = [lib.ekb200_host_cyclic_global_col(LL(lc), LL(nb), P, r) for lc in range(nloc)]
+        # ScaLAPACK's INDXL2G for every local column
+        assert cols == [((lc // nb) * P + r) * nb + lc % nb for lc in range(nloc)]
+        assert all(0 <= c < n_vec for c in cols)
+        owned += cols
+    assert sorted(owned) == list(range(n_vec))               # every column delivered exactly once

@@ -9,6 +9,8 @@ wavefront, every task of a wavefront reading a SNAPSHOT of the band taken when t
 can never profit from a write of a task it is not ordered after), and checks that
   * the result is tridiagonal with the spectrum of the band matrix,
   * the reflectors (V2, TAU2 in the kernel's layout) reproduce it: Q2^T B Q2 = T,
+  * the deferred part of the D block (every column but the first is stored only AFTER the task's completion count
+    has been published, so that the release does not wait for it) is never read before the next count covers it,
   * concurrent tasks write disjoint elements (the L block of task t is stored WITHOUT its (0, 0) element: that beta
     went to the band with the look-ahead of task t-1 and may already have been consumed and overwritten).
 It is a test of the ALGORITHM (index ranges, dependency distance); the kernel itself is checked on the GPU by
@@ -55,7 +57,7 @@ class Band:
         return M
 
 
-def run_schedule(A, b, lag):
+def run_schedule(A, b, lag, defer_d=True):
     """Replay the kernel's schedule.  Returns (band object, V2, TAU2, max writers per element per wavefront)."""
     n = A.shape[0]
     band = Band(A, b)
@@ -89,12 +91,15 @@ def run_schedule(A, b, lag):
 
         snap = _Snap()
 
-        def put(i, j, val, tag):
+        def put(i, j, val, tag, visible_with=None):
+            """visible_with: the task whose completion count first covers this store (deferred stores: the columns
+            of D other than the first go to the band only after the task's own count has been published, so for the
+            ordering check they belong to the NEXT task of the sweep)."""
             key = (i, j)
             if key in writes:
                 raise AssertionError(f"wavefront {k}: element {key} written by {writes[key]} and {tag}")
             writes[key] = tag
-            acc.setdefault(key, []).append((*tag, True))
+            acc.setdefault(key, []).append((*(visible_with or tag), True))
             AB[i - j, j] = val
 
         for s in range(nsweep):
@@ -145,7 +150,8 @@ def run_schedule(A, b, lag):
                 D = D - np.outer(v[:nr], w) - np.outer(w, v[:nr])
                 for jj in range(nr):
                     for ii in range(jj, nr):
-                        put(r0 + ii, r0 + jj, D[ii, jj], (s, t))
+                        late = defer_d and jj > 0 and t + 1 < nt
+                        put(r0 + ii, r0 + jj, D[ii, jj], (s, t), (s, t + 1) if late else None)
                 u = tau * (Bk @ v[:nr])
                 Bk = Bk - np.outer(u, v[:nr])
                 if t + 1 >= nt:
