@@ -404,10 +404,12 @@ def run_ours(args) -> None:
             e_wall = float(t.item())
         assert np.all(np.isfinite(hw)) and np.all(np.diff(hw) >= 0)
         e2e = {"value": K * canonical_flops(n) / e_wall / 1e12, "unit": UNIT,
-               "h2d_bytes_per_step": world * 2 * n * n * 8, "d2h_bytes_per_step": n * n * 8 + world * n * 8,
+               "h2d_bytes_per_step": 2 * n * n * 8, "d2h_bytes_per_step": n * n * 8 + world * n * 8,
                "seconds_per_step": e_wall / K, "host_buffers": "pinned",
-               "note": "every rank uploads the replicated A and B (as the reference hands every rank the replicated "
-                       "COO) and downloads its column slab of the eigenvectors" if world > 1 else "single rank"}
+               "note": "every rank holds the replicated host A and B (as the reference hands every rank the replicated "
+                       "COO) but uploads only its n/P block of columns of each; the blocks are all-gathered over NVLink; "
+                       "every rank downloads all eigenvalues and its column slab of the eigenvectors"
+                       if world > 1 else "single rank"}
         for p in hp:
             ctx.call("ekb200_host_free", p)
 

@@ -85,6 +85,9 @@ int ekb200_destroy(ekb200_ctx* h) {
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->d_info) cudaFree(ctx->d_info);
   if (ctx->h_info) cudaFreeHost(ctx->h_info);
+  if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
+  for (auto& e : ctx->aux_ev)
+    if (e) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->stream);
   delete h;
   return 0;
@@ -143,6 +146,11 @@ int ekb200_set_option(ekb200_ctx* h, const char* key, int64_t value) {
   if (!strcmp(key, "out_block")) {  // block size NB of the caller's 1 x P block-cyclic eigenvector descriptor (0: slabs)
     if (value < 0) return -3;
     ctx->out_block = value;
+    return 0;
+  }
+  if (!strcmp(key, "sy2sb_lookahead")) {  // panel look-ahead of the dense-to-band reduction (tuning; default 1)
+    if (value != 0 && value != 1) return -3;
+    ctx->sy2sb_lookahead = (int)value;
     return 0;
   }
   if (!strcmp(key, "q2_kc")) {
@@ -555,19 +563,28 @@ static int solve_host(ekb200_ctx* h, int64_t n, int64_t nev, const double* A, in
   {
     StageTimer t(ctx, hasB ? "solve_with_general_b200:setup_matrices" : "eigen_solver_b200:setup_matrices");
     cudaError_t ce = cudaSuccess;
-    if (cooA) {
-      rc = ekb200_coo_to_dense(h, n, cooA->nnz, cooA->ij, cooA->v, dA, ld);
-    } else {
-      ce = cudaMemcpy2DAsync(dA, ld * 8, A, lda * 8, n * 8, n, cudaMemcpyHostToDevice, ctx->stream);
-      if (ce == cudaSuccess) rc = symmetrize_from_lower(ctx, dA, ld, n);
-    }
-    if (!rc && ce == cudaSuccess && hasB) {
-      if (cooB) {
-        rc = ekb200_coo_to_dense(h, n, cooB->nnz, cooB->ij, cooB->v, dB, ld);
+    // Dense host matrices on P > 1 ranks: every rank holds the same (replicated) arrays, so each uploads only ITS
+    // block of columns over PCIe (n^2 / P elements per matrix) and the blocks are all-gathered over NVLink -- the
+    // counterpart of distribute_matrix.f90:92-148, where a process only ever touches its n^2 / P piece.
+    std::vector<i64> ub;
+    slab_bounds(n, ctx->nranks, 128, ub);
+    const i64 u0 = ub[ctx->rank], uk = ub[ctx->rank + 1] - ub[ctx->rank];
+    auto upload = [&](const double* H, i64 ldh, double* D) -> int {
+      if (ctx->nranks == 1) {
+        ce = cudaMemcpy2DAsync(D, ld * 8, H, ldh * 8, n * 8, n, cudaMemcpyHostToDevice, ctx->stream);
       } else {
-        ce = cudaMemcpy2DAsync(dB, ld * 8, B, ldb * 8, n * 8, n, cudaMemcpyHostToDevice, ctx->stream);
-        if (ce == cudaSuccess) rc = symmetrize_from_lower(ctx, dB, ld, n);
+        if (uk > 0)
+          ce = cudaMemcpy2DAsync(D + u0 * ld, ld * 8, H + u0 * ldh, ldh * 8, n * 8, uk, cudaMemcpyHostToDevice, ctx->stream);
+        if (ce == cudaSuccess) EKB_TRY(comm_allgather_cols(ctx, D, ld, ub));
       }
+      if (ce != cudaSuccess) return 0;
+      return symmetrize_from_lower(ctx, D, ld, n);
+    };
+    if (cooA) rc = ekb200_coo_to_dense(h, n, cooA->nnz, cooA->ij, cooA->v, dA, ld);
+    else rc = upload(A, lda, dA);
+    if (!rc && ce == cudaSuccess && hasB) {
+      if (cooB) rc = ekb200_coo_to_dense(h, n, cooB->nnz, cooB->ij, cooB->v, dB, ld);
+      else rc = upload(B, ldb, dB);
     }
     if (ce != cudaSuccess) {
       ctx->last_cuda = ce;

@@ -36,6 +36,8 @@ struct Ctx {
   int device = 0;
   int num_sms = 148;
   cudaStream_t stream = nullptr;
+  cudaStream_t aux_stream = nullptr;  // high-priority side stream (panel look-ahead of sy2sb); created on first use
+  cudaEvent_t aux_ev[2] = {nullptr, nullptr};
   std::vector<Event> events;          // timing table replayed through add_event by the caller
   std::vector<void*> allocs;          // every device allocation handed out and not yet released
   std::vector<std::pair<void*, size_t>> live;   // ... with its (rounded) size
@@ -57,6 +59,7 @@ struct Ctx {
   int sb2st_rwarp = 1;                // 1: one extra warp forms the reflectors beside the updates; 0: warp 0 does
   int sb2st_cps = 0;                  // cap on resident CTAs per SM (0 = what the occupancy calculator allows)
   long long out_block = 0;            // > 0: host entry points deliver the 1 x P block-cyclic piece with this block size (layout.h)
+  int sy2sb_lookahead = 1;            // 1: factor panel p+1 on the side stream while the rank-2b update of panel p runs
   int q2_kc = 0;                      // columns of Z per CTA in apply_q2 (0 = choose; 64|80|96|112|128)
   // stage timers
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;

@@ -257,6 +257,24 @@ size_t sy2sb_workspace_doubles(i64 n, int b, int num_sms) {
          + (size_t)2 * num_sms * 64 + 8 * 64 * 64;
 }
 
+// Work issued inside this scope goes to the context's side stream (and records its profile events there).
+namespace {
+struct OnAuxStream {
+  Ctx* ctx;
+  cudaStream_t saved;
+  explicit OnAuxStream(Ctx* c) : ctx(c), saved(c->stream) { c->stream = c->aux_stream; }
+  ~OnAuxStream() { ctx->stream = saved; }
+};
+}  // namespace
+
+// Panel look-ahead.  The Householder QR of a panel is a latency chain (one grid barrier per column, ~0.1 TFLOP/s):
+// run after the trailing update it idles the whole chip for 0.6 s of a 2.8 s reduction at n = 32768.  But panel p+1
+// only needs ITS b columns of the trailing matrix updated, so per panel
+//   main stream:  W_p (SYMM etc.) -> skinny update of the next panel's columns -> [event] -> rank-2b update of the rest
+//   side stream:                                             [wait] QR, band extraction, T of panel p+1 -> [event]
+// and the main stream waits for that event before the SYMM of panel p+1.  The QR grid is kept small (it is bound by
+// its barriers, not by throughput), so the big update keeps > 90 % of the SMs; the side stream has the higher priority
+// so that the QR's CTAs take the first SMs that fall free.
 int sy2sb(Ctx* ctx, i64 n, int b, double* A, i64 lda, double* AB, i64 ldab, double* T1, double* work) {
   if (n <= 0) return 0;
   const i64 ldp = round_up(n, 8);
@@ -271,33 +289,64 @@ int sy2sb(Ctx* ctx, i64 n, int b, double* A, i64 lda, double* AB, i64 ldab, doub
   double* S = Gm + 64 * 64;          // b*b
   double* TS = S + 64 * 64;          // b*b
 
-  i64 j = 0;
-  int p = 0;
-  for (;; j += b, ++p) {
-    const i64 m = n - j - b;
-    if (m < 2) break;
-    double* P = A + j * lda + (j + b);
-    double* A22 = A + (j + b) * lda + (j + b);
-    double* T = T1 + (size_t)p * b * b;
-    // 1. panel QR
-    {
-      int G = (int)((m + QR_THREADS - 1) / QR_THREADS);
-      if (G > ctx->num_sms) G = ctx->num_sms;
-      int mi = (int)m;
-      EKB_TRY(launch_panel_qr(ctx, b, P, lda, mi, tau, Rout, partial, G));
+  bool lookahead = ctx->sy2sb_lookahead != 0 && n - b >= 4 * b;
+  if (lookahead && !ctx->aux_stream) {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);  // hi = numerically lowest = highest priority
+    if (cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, hi) != cudaSuccess) {
+      cudaGetLastError();
+      ctx->aux_stream = nullptr;
+      lookahead = false;
     }
-    // 2. band extraction + explicit V
+  }
+  for (auto& e : ctx->aux_ev)
+    if (lookahead && !e && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) {
+      cudaGetLastError();
+      lookahead = false;
+    }
+
+  // QR + band extraction + T of the panel at column j (m rows below the band), on the CURRENT ctx->stream
+  auto factor_panel = [&](i64 j, int p, bool side) -> int {
+    const i64 m = n - j - b;
+    double* P = A + j * lda + (j + b);
+    double* T = T1 + (size_t)p * b * b;
+    int G = (int)((m + QR_THREADS - 1) / QR_THREADS);
+    if (G > ctx->num_sms) G = ctx->num_sms;
+    if (side) {  // beside the trailing update: a few CTAs (8 rows per thread and column step), never more than 1/8 of the chip
+      int gs = (int)((m + 8 * QR_THREADS - 1) / (8 * QR_THREADS));
+      gs = std::max(gs, 2);
+      gs = std::min(gs, std::max(ctx->num_sms / 8, 1));
+      G = std::min(G, gs);
+    }
+    EKB_TRY(launch_panel_qr(ctx, b, P, lda, (int)m, tau, Rout, partial, G));
     fixup_extract_kernel<<<1, 256, 0, ctx->stream>>>(A, lda, n, j, b, Rout, AB, ldab); EKB_COUNT_LAUNCH(ctx);
     EKB_CUDA(cudaGetLastError());
-    // 3. T from Gram matrix
     GemmP g;
     g.m = b; g.n = b; g.k = (int)m; g.A = P; g.lda = lda; g.B = P; g.ldb = lda; g.C = Gm; g.ldc = b;
     g.alpha = 1.0; g.beta = 0.0;
     EKB_TRY(gemm(ctx, GEMM_TA, g, -1, pick_splitk(ctx, b, b, m, 128, 64)));
     build_T_kernel<<<1, 64, 0, ctx->stream>>>(Gm, tau, b, T); EKB_COUNT_LAUNCH(ctx);
     EKB_CUDA(cudaGetLastError());
+    return 0;
+  };
+
+  i64 j = 0;
+  int p = 0;
+  bool factored = false;  // panel p already factored (on the side stream; ctx->aux_ev[0] marks its completion)
+  for (;; j += b, ++p) {
+    const i64 m = n - j - b;
+    if (m < 2) break;
+    double* P = A + j * lda + (j + b);
+    double* A22 = A + (j + b) * lda + (j + b);
+    double* T = T1 + (size_t)p * b * b;
+    // 1.-3. panel QR, band extraction + explicit V, T
+    if (factored) EKB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->aux_ev[0], 0));
+    else EKB_TRY(factor_panel(j, p, false));
+    factored = false;
     // 4. W0 = A22 V (symmetric, lower stored) -> VW[:, b:2b) as scratch ; X = W0 T
+    GemmP g;
     double* W0 = WV;  // scratch m x b
+    g.alpha = 1.0; g.beta = 0.0;
     g.m = (int)m; g.n = b; g.k = (int)m; g.A = A22; g.lda = lda; g.B = P; g.ldb = lda; g.C = W0; g.ldc = ldp;
     EKB_TRY(gemm(ctx, GEMM_SYMA, g, -1, pick_splitk(ctx, m, b, m, 128, 64)));
     g.m = (int)m; g.n = b; g.k = b; g.A = W0; g.lda = ldp; g.B = T; g.ldb = b; g.C = X; g.ldc = ldp;
@@ -313,10 +362,30 @@ int sy2sb(Ctx* ctx, i64 n, int b, double* A, i64 lda, double* AB, i64 ldab, doub
     // 5. A22 -= [V W][W V]^T
     pack_vw_kernel<<<dim3(cdiv(m, 256), b), 256, 0, ctx->stream>>>(P, lda, X, ldp, (int)m, b, VW, WV, ldp); EKB_COUNT_LAUNCH(ctx);
     EKB_CUDA(cudaGetLastError());
-    g.m = (int)m; g.n = (int)m; g.k = 2 * b; g.A = VW; g.lda = ldp; g.B = WV; g.ldb = ldp; g.C = A22; g.ldc = lda;
     g.alpha = -1.0; g.beta = 1.0;
-    EKB_TRY(gemm(ctx, GEMM_TB, g, /*tri_keep=*/128));
+    const i64 mnext = m - b;  // rows of the next panel
+    if (lookahead && mnext >= 2 && m > 2 * b) {
+      // 5a. the next panel's columns (and the diagonal block above them) first ...
+      g.m = (int)m; g.n = b; g.k = 2 * b; g.A = VW; g.lda = ldp; g.B = WV; g.ldb = ldp; g.C = A22; g.ldc = lda;
+      EKB_TRY(gemm(ctx, GEMM_TB, g));
+      EKB_CUDA(cudaEventRecord(ctx->aux_ev[1], ctx->stream));
+      {  // ... so that panel p+1 is factored on the side stream ...
+        OnAuxStream aux(ctx);
+        EKB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->aux_ev[1], 0));
+        EKB_TRY(factor_panel(j + b, p + 1, true));
+        EKB_CUDA(cudaEventRecord(ctx->aux_ev[0], ctx->stream));
+      }
+      factored = true;
+      // 5b. ... while the rest of the trailing matrix (lower tiles + one tile diagonal of A22[b:, b:]) is updated here
+      g.m = (int)(m - b); g.n = (int)(m - b); g.k = 2 * b; g.A = VW + b; g.lda = ldp; g.B = WV + b; g.ldb = ldp;
+      g.C = A22 + (i64)b * lda + b; g.ldc = lda;
+      EKB_TRY(gemm(ctx, GEMM_TB, g, /*tri_keep=*/128));
+    } else {
+      g.m = (int)m; g.n = (int)m; g.k = 2 * b; g.A = VW; g.lda = ldp; g.B = WV; g.ldb = ldp; g.C = A22; g.ldc = lda;
+      EKB_TRY(gemm(ctx, GEMM_TB, g, /*tri_keep=*/128));
+    }
   }
+  if (factored) EKB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->aux_ev[0], 0));  // (cannot happen: the last panel has no successor)
   // tail columns
   if (j < n) {
     extract_tail_kernel<<<(unsigned)(n - j), 128, 0, ctx->stream>>>(A, lda, n, j, b, AB, ldab); EKB_COUNT_LAUNCH(ctx);
