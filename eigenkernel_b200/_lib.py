@@ -10,7 +10,8 @@ import os
 from ctypes import POINTER, byref, c_char, c_char_p, c_double, c_int, c_int32, c_int64, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libekb200.so")
+# EKB200_LIB: an alternative build of the same C-ABI (experiments with build-time variants; tests and bench use the default)
+LIB_PATH = os.environ.get("EKB200_LIB") or os.path.join(_HERE, "libekb200.so")
 
 _dp = POINTER(c_double)
 

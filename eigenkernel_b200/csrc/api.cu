@@ -148,6 +148,16 @@ int ekb200_set_option(ekb200_ctx* h, const char* key, int64_t value) {
     ctx->out_block = value;
     return 0;
   }
+  if (!strcmp(key, "gemm_bulk")) {  // TMA-fed warp-specialised GEMM kernel for the big-tile products (tuning)
+    if (value != 0 && value != 1) return -3;
+    ctx->gemm_bulk = (int)value;
+    return 0;
+  }
+  if (!strcmp(key, "panel_qr_variant")) {  // 1 shared-memory-resident panel QR (default) | 0 global-memory kernel
+    if (value != 0 && value != 1) return -3;
+    ctx->panel_qr_variant = (int)value;
+    return 0;
+  }
   if (!strcmp(key, "sy2sb_lookahead")) {  // panel look-ahead of the dense-to-band reduction (tuning; default 1)
     if (value != 0 && value != 1) return -3;
     ctx->sy2sb_lookahead = (int)value;

@@ -59,7 +59,9 @@ struct Ctx {
   int sb2st_rwarp = 1;                // 1: one extra warp forms the reflectors beside the updates; 0: warp 0 does
   int sb2st_cps = 0;                  // cap on resident CTAs per SM (0 = what the occupancy calculator allows)
   long long out_block = 0;            // > 0: host entry points deliver the 1 x P block-cyclic piece with this block size (layout.h)
-  int sy2sb_lookahead = 1;            // 1: factor panel p+1 on the side stream while the rank-2b update of panel p runs
+  int gemm_bulk = 0;                  // 1: big-tile products run on the TMA-fed warp-specialised GEMM kernel (gemm.cu)
+  int panel_qr_variant = 1;           // 1: panel QR with the panel resident in shared memory; 0: the round-1 global-memory kernel
+  int sy2sb_lookahead = 0;            // 1: factor panel p+1 on the side stream while the rank-2b update of panel p runs (measured: a loss, see sy2sb.cu)
   int q2_kc = 0;                      // columns of Z per CTA in apply_q2 (0 = choose; 64|80|96|112|128)
   // stage timers
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -138,7 +140,8 @@ enum GemmFlags {
 // computed (whole tiles above that region are skipped): 1 = lower triangle, 128 = lower + a 128 band.
 int gemm(Ctx* ctx, int flags, const GemmP& p, int tri_keep = -1, int splitk = 1);
 // Batched: `batch` is a DEVICE array of nb problems; (max_m, max_n) bound the grid.
-int gemm_batched(Ctx* ctx, int flags, const GemmP* d_batch, int nb, int max_m, int max_n);
+// k_hint: typical k-depth of the batch (the descriptors live on the device): >= 1024 selects the deep pipeline geometry.
+int gemm_batched(Ctx* ctx, int flags, const GemmP* d_batch, int nb, int max_m, int max_n, int k_hint = 0);
 int gemm_profile_collect(Ctx* ctx, double* seconds, double* flops, long long* launches);
 // Per-launch CUDA-event brackets in "profile_gemm" mode, tagged by kernel family (roofline evidence measured
 // live inside bench.py).  prof_begin/prof_end are no-ops when profiling is off.

@@ -19,10 +19,12 @@
 
 namespace ekb {
 
-constexpr int BK = 16;
-constexpr int LDK = BK + 4;  // K-major row stride
+// Pipeline geometry = (BK, STAGES): k-depth of a stage and number of stages, template parameters of the kernel.  Two
+// are instantiated: (16, 4) -- short prologue, best when K is small (the K = 2b updates of dense-to-band run only 8
+// k-tiles) -- and (32, 3) -- half as many block barriers per DMMA; measured +3 % on 8192^3 and +9 % on the N = 64
+// panel products, -14 % on the K = 128 update (profiles/r02_gemm_shapes_*.jsonl).  K-major row stride BK + 4 doubles
+// (8 words mod 32: conflict-free 64-bit fragment loads per half warp for both values of BK).
 constexpr int GEMM_THREADS = 256;
-constexpr int GEMM_STAGES = 4;
 
 __device__ __forceinline__ void cp_async16(double* smem, const double* g, int bytes) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -45,9 +47,10 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 
 // Load one (BMN x BK) operand tile.  Element (mn, k) lives at g[(mn0+mn) * s_mn + (k0+k) * s_k] where
 // exactly one of the two global strides is 1 (kmajor: s_k == 1).
-template <int BMN>
+template <int BMN, int BK>
 __device__ __forceinline__ void load_tile(double* s, const double* __restrict__ g, i64 ld, bool kmajor, bool al16,
                                           int mn0, int k0, int mn_lim, int k_lim, int tid) {
+  constexpr int LDK = BK + 4;
   if (kmajor) {
     if (al16) {
 #pragma unroll
@@ -98,13 +101,14 @@ __device__ __forceinline__ void load_tile(double* s, const double* __restrict__ 
 __device__ __forceinline__ void cp_async16_full(unsigned s, const double* g) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(g) : "memory");
 }
-template <int BMN>
+template <int BMN, int BK>
 __device__ __forceinline__ void load_tile_fast_km(unsigned dst, const double* __restrict__ src, i64 ld) {
+  constexpr int LDK = BK + 4;
   constexpr int RPP = GEMM_THREADS / (BK / 2);  // tile rows (mn) covered per pass
 #pragma unroll
   for (int q = 0; q < BMN / RPP; ++q) cp_async16_full(dst + q * RPP * LDK * 8, src + (i64)q * RPP * ld);
 }
-template <int BMN>
+template <int BMN, int BK>
 __device__ __forceinline__ void load_tile_fast_mn(unsigned dst, const double* __restrict__ src, i64 ld) {
   constexpr int KPP = GEMM_THREADS / (BMN / 2);  // k rows covered per pass
 #pragma unroll
@@ -112,9 +116,10 @@ __device__ __forceinline__ void load_tile_fast_mn(unsigned dst, const double* __
 }
 
 // One k-tile of DMMAs with compile-time shared-memory strides (immediate LDS offsets, no address arithmetic).
-template <int MI, int NI, int BM, int BN, bool AKM, bool BKM>
+template <int MI, int NI, int BM, int BN, int BK, bool AKM, bool BKM>
 __device__ __forceinline__ void mma_ktile(double (&acc)[MI][NI][2], const double* __restrict__ tA,
                                           const double* __restrict__ tB) {
+  constexpr int LDK = BK + 4;
   constexpr int a_smn = AKM ? LDK : 1, a_sk = AKM ? 1 : (BM + 4);
   constexpr int b_smn = BKM ? LDK : 1, b_sk = BKM ? 1 : (BN + 4);
 #pragma unroll
@@ -131,10 +136,11 @@ __device__ __forceinline__ void mma_ktile(double (&acc)[MI][NI][2], const double
   }
 }
 
-template <int BM, int BN, int WM, int WN, bool BATCHED>
+template <int BM, int BN, int WM, int WN, bool BATCHED, int BK, int GEMM_STAGES>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(GemmP p0, const GemmP* __restrict__ batch, int flags, int tri_keep, int splitk, double* __restrict__ ws) {
   extern __shared__ __align__(16) double smem[];
+  constexpr int LDK = BK + 4;
   constexpr int A_TILE = BM * LDK;  // >= BK*(BM+4)
   constexpr int B_TILE = BN * LDK;
   constexpr int MI = WM / 8, NI = WN / 8;
@@ -195,17 +201,17 @@ gemm_kernel(GemmP p0, const GemmP* __restrict__ batch, int flags, int tri_keep, 
     const bool akm = a_is_kmajor(kt);
     if (a_full && kfull) {
       const unsigned st = sA32 + (unsigned)(stage * A_TILE) * 8u;
-      if (akm) load_tile_fast_km<BM>(st + a_s_km, p.A + a_g_km + k0, p.lda);
-      else load_tile_fast_mn<BM>(st + a_s_mn, p.A + a_g_mn + (i64)k0 * p.lda, p.lda);
+      if (akm) load_tile_fast_km<BM, BK>(st + a_s_km, p.A + a_g_km + k0, p.lda);
+      else load_tile_fast_mn<BM, BK>(st + a_s_mn, p.A + a_g_mn + (i64)k0 * p.lda, p.lda);
     } else {
-      load_tile<BM>(sA + stage * A_TILE, p.A, p.lda, akm, al16, m0, k0, p.m, p.k, tid);
+      load_tile<BM, BK>(sA + stage * A_TILE, p.A, p.lda, akm, al16, m0, k0, p.m, p.k, tid);
     }
     if (b_full && kfull) {
       const unsigned st = sB32 + (unsigned)(stage * B_TILE) * 8u;
-      if (b_kmajor) load_tile_fast_km<BN>(st + b_s, p.B + b_g + k0, p.ldb);
-      else load_tile_fast_mn<BN>(st + b_s, p.B + b_g + (i64)k0 * p.ldb, p.ldb);
+      if (b_kmajor) load_tile_fast_km<BN, BK>(st + b_s, p.B + b_g + k0, p.ldb);
+      else load_tile_fast_mn<BN, BK>(st + b_s, p.B + b_g + (i64)k0 * p.ldb, p.ldb);
     } else {
-      load_tile<BN>(sB + stage * B_TILE, p.B, p.ldb, b_kmajor, al16, n0, k0, p.n, p.k, tid);
+      load_tile<BN, BK>(sB + stage * B_TILE, p.B, p.ldb, b_kmajor, al16, n0, k0, p.n, p.k, tid);
     }
   };
 
@@ -286,11 +292,11 @@ gemm_kernel(GemmP p0, const GemmP* __restrict__ batch, int flags, int tri_keep, 
     const double* tA = sA + stage * A_TILE + (akm ? a_t_km : a_t_mn);
     const double* tB = sB + stage * B_TILE + b_t;
     if (akm) {
-      if (b_kmajor) mma_ktile<MI, NI, BM, BN, true, true>(acc, tA, tB);
-      else mma_ktile<MI, NI, BM, BN, true, false>(acc, tA, tB);
+      if (b_kmajor) mma_ktile<MI, NI, BM, BN, BK, true, true>(acc, tA, tB);
+      else mma_ktile<MI, NI, BM, BN, BK, true, false>(acc, tA, tB);
     } else {
-      if (b_kmajor) mma_ktile<MI, NI, BM, BN, false, true>(acc, tA, tB);
-      else mma_ktile<MI, NI, BM, BN, false, false>(acc, tA, tB);
+      if (b_kmajor) mma_ktile<MI, NI, BM, BN, BK, false, true>(acc, tA, tB);
+      else mma_ktile<MI, NI, BM, BN, BK, false, false>(acc, tA, tB);
     }
   }
   cp_async_wait<0>();
@@ -336,6 +342,219 @@ gemm_kernel(GemmP p0, const GemmP* __restrict__ batch, int flags, int tri_keep, 
   }
 }
 
+// ------------------------------------------------------------------------------------------ TMA-fed variant
+// Warp-specialised form of the same tile computation (round 2): ONE producer warp feeds the shared-memory ring with
+// bulk asynchronous copies (cp.async.bulk.shared::cluster.global, the TMA engine; SASS UBLKCP) that complete on an
+// mbarrier per stage; the eight consumer warps wait on that barrier, issue nothing but fragment loads and DMMAs, and
+// hand the stage back through a second mbarrier.  Compared with the LDGSTS kernel above the consumers lose 16 copy
+// instructions + their address arithmetic per k-tile and, more importantly, the block-wide barrier per k-tile.
+// Operand tiles land in the SAME padded layouts (one copy per k-contiguous row of a K-major tile, or per k-row of an
+// MN-major one: the destination of a 1-D bulk copy is free, a tensor-map box would land dense and conflict 4-way).
+// Partial tiles: rows beyond the matrix are never copied and stay at the zeros written once before the first copy.
+// Used for non-batched, non-split, non-symmetric products with 16-byte aligned operands and k a multiple of BK.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+constexpr int BULK_CONSUMER_WARPS = 8;
+constexpr int BULK_THREADS = 32 * (BULK_CONSUMER_WARPS + 1);
+
+template <int BM, int BN, int WM, int WN, int BK, int STAGES>
+__global__ void __launch_bounds__(BULK_THREADS, 1) gemm_bulk_kernel(GemmP p, int flags, int tri_keep) {
+  extern __shared__ __align__(16) double smem[];
+  constexpr int LDK = BK + 4;
+  constexpr int A_TILE = BM * LDK;  // >= BK*(BM+4)
+  constexpr int B_TILE = BN * LDK;
+  constexpr int MI = WM / 8, NI = WN / 8;
+  constexpr int WARPS_M = BM / WM;
+  static_assert((BM / WM) * (BN / WN) == BULK_CONSUMER_WARPS, "8 consumer warps");
+  __shared__ unsigned long long full_bar[STAGES], empty_bar[STAGES];
+
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  if (m0 >= p.m || n0 >= p.n) return;
+  if (tri_keep >= 0 && n0 - (m0 + BM - 1) >= tri_keep) return;
+  const int nk = p.k / BK;
+  const bool ta = flags & GEMM_TA, tb = flags & GEMM_TB;
+  const bool b_kmajor = !tb;
+  double* sA = smem;
+  double* sB = smem + STAGES * A_TILE;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rowsA = min(BM, p.m - m0), rowsB = min(BN, p.n - n0);
+
+  if (tid == 0) {
+#pragma unroll
+    for (int st = 0; st < STAGES; ++st) {
+      mbar_init(&full_bar[st], 1);
+      mbar_init(&empty_bar[st], BULK_CONSUMER_WARPS);
+    }
+  }
+  if (rowsA < BM || rowsB < BN) {  // partial tile: the rows no copy ever touches must read as zeros
+    for (int e = tid; e < STAGES * (A_TILE + B_TILE); e += BULK_THREADS) smem[e] = 0.0;
+  }
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  __syncthreads();
+
+  if (warp == BULK_CONSUMER_WARPS) {
+    // ---------------- producer warp
+    const unsigned bytes = (unsigned)(rowsA + rowsB) * BK * 8u;
+    for (int it = 0; it < nk; ++it) {
+      const int stage = it % STAGES;
+      if (it >= STAGES) mbar_wait(&empty_bar[stage], (unsigned)((it / STAGES - 1) & 1));
+      if (lane == 0) mbar_arrive_expect_tx(&full_bar[stage], bytes);
+      __syncwarp();
+      const i64 k0 = (i64)it * BK;
+      double* dA = sA + stage * A_TILE;
+      double* dB = sB + stage * B_TILE;
+      if (ta) {
+        for (int r = lane; r < rowsA; r += 32) bulk_g2s(dA + r * LDK, p.A + (i64)(m0 + r) * p.lda + k0, BK * 8u, &full_bar[stage]);
+      } else {
+        for (int kk = lane; kk < BK; kk += 32)
+          bulk_g2s(dA + kk * (BM + 4), p.A + (k0 + kk) * p.lda + m0, (unsigned)rowsA * 8u, &full_bar[stage]);
+      }
+      if (b_kmajor) {
+        for (int r = lane; r < rowsB; r += 32) bulk_g2s(dB + r * LDK, p.B + (i64)(n0 + r) * p.ldb + k0, BK * 8u, &full_bar[stage]);
+      } else {
+        for (int kk = lane; kk < BK; kk += 32)
+          bulk_g2s(dB + kk * (BN + 4), p.B + (k0 + kk) * p.ldb + n0, (unsigned)rowsB * 8u, &full_bar[stage]);
+      }
+    }
+    return;
+  }
+
+  // ---------------- consumer warps
+  const int wm = warp % WARPS_M, wn = warp / WARPS_M;
+  const int lq = lane >> 2, lr = lane & 3;
+  double alpha = p.alpha, beta = p.beta;
+  double* C = p.C;
+  const i64 ldc = p.ldc;
+  double acc[MI][NI][2];
+#pragma unroll
+  for (int i = 0; i < MI; ++i)
+#pragma unroll
+    for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  const bool cvec = (((uintptr_t)C & 15) == 0) && ((ldc & 1) == 0);
+  const bool interior = cvec && rowsA == BM && rowsB == BN;
+  if (beta != 0.0 && (alpha == 1.0 || alpha == -1.0)) {  // acc = alpha beta C (see gemm_kernel)
+    const double sc = alpha * beta;
+    if (interior) {
+      const double* cbase = C + (i64)(n0 + wn * WN + lq) * ldc + (m0 + wm * WM + 2 * lr);
+      double2 old[MI][NI];
+#pragma unroll
+      for (int j = 0; j < NI; ++j)
+#pragma unroll
+        for (int i = 0; i < MI; ++i) old[i][j] = __ldcg(reinterpret_cast<const double2*>(cbase + (i64)(j * 8) * ldc + i * 8));
+#pragma unroll
+      for (int j = 0; j < NI; ++j)
+#pragma unroll
+        for (int i = 0; i < MI; ++i) {
+          acc[i][j][0] = sc * old[i][j].x;
+          acc[i][j][1] = sc * old[i][j].y;
+        }
+    } else {
+#pragma unroll
+      for (int j = 0; j < NI; ++j) {
+        const int col = n0 + wn * WN + j * 8 + lq;
+        if (col >= p.n) continue;
+#pragma unroll
+        for (int i = 0; i < MI; ++i) {
+          const int row = m0 + wm * WM + i * 8 + 2 * lr;
+          if (row >= p.m) continue;
+          const double* cp = C + (i64)col * ldc + row;
+          acc[i][j][0] = sc * cp[0];
+          if (row + 1 < p.m) acc[i][j][1] = sc * cp[1];
+        }
+      }
+    }
+    beta = 0.0;
+  }
+  const int a_t = ta ? (wm * WM + lq) * LDK + lr : (wm * WM + lq) + lr * (BM + 4);
+  const int b_t = b_kmajor ? (wn * WN + lq) * LDK + lr : (wn * WN + lq) + lr * (BN + 4);
+  for (int it = 0; it < nk; ++it) {
+    const int stage = it % STAGES;
+    mbar_wait(&full_bar[stage], (unsigned)((it / STAGES) & 1));
+    const double* tA = sA + stage * A_TILE + a_t;
+    const double* tB = sB + stage * B_TILE + b_t;
+    if (ta) {
+      if (b_kmajor) mma_ktile<MI, NI, BM, BN, BK, true, true>(acc, tA, tB);
+      else mma_ktile<MI, NI, BM, BN, BK, true, false>(acc, tA, tB);
+    } else {
+      if (b_kmajor) mma_ktile<MI, NI, BM, BN, BK, false, true>(acc, tA, tB);
+      else mma_ktile<MI, NI, BM, BN, BK, false, false>(acc, tA, tB);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[stage]);
+  }
+  // epilogue
+  if (interior && beta == 0.0) {
+    double* cbase = C + (i64)(n0 + wn * WN + lq) * ldc + (m0 + wm * WM + 2 * lr);
+#pragma unroll
+    for (int j = 0; j < NI; ++j)
+#pragma unroll
+      for (int i = 0; i < MI; ++i)
+        *reinterpret_cast<double2*>(cbase + (i64)(j * 8) * ldc + i * 8) = make_double2(alpha * acc[i][j][0], alpha * acc[i][j][1]);
+    return;
+  }
+#pragma unroll
+  for (int j = 0; j < NI; ++j) {
+    const int col = n0 + wn * WN + j * 8 + lq;
+    if (col >= p.n) continue;
+#pragma unroll
+    for (int i = 0; i < MI; ++i) {
+      const int row = m0 + wm * WM + i * 8 + 2 * lr;
+      if (row >= p.m) continue;
+      double* cp = C + (i64)col * ldc + row;
+      double v0 = alpha * acc[i][j][0], v1 = alpha * acc[i][j][1];
+      if (beta != 0.0) {
+        v0 += beta * cp[0];
+        if (row + 1 < p.m) v1 += beta * cp[1];
+      }
+      cp[0] = v0;
+      if (row + 1 < p.m) cp[1] = v1;
+    }
+  }
+}
+
+template <int BM, int BN, int WM, int WN, int BK, int STAGES>
+static int launch_bulk(Ctx* ctx, int flags, const GemmP& p, int tri_keep) {
+  constexpr size_t smem = (size_t)STAGES * (BM + BN) * (BK + 4) * sizeof(double);
+  static bool attr_dev[64] = {};
+  bool& attr_set = attr_dev[ctx->device & 63];
+  auto kern = gemm_bulk_kernel<BM, BN, WM, WN, BK, STAGES>;
+  if (!attr_set) {
+    EKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  dim3 grid(cdiv(p.m, BM), cdiv(p.n, BN), 1);
+  kern<<<grid, BULK_THREADS, smem, ctx->stream>>>(p, flags, tri_keep); EKB_COUNT_LAUNCH(ctx);
+  EKB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 __global__ void splitk_reduce_kernel(const double* __restrict__ ws, int splitk, int m, int n, double* __restrict__ C,
                                      i64 ldc, double alpha, double beta, int tri_keep) {
   i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -350,13 +569,14 @@ __global__ void splitk_reduce_kernel(const double* __restrict__ ws, int splitk, 
   *cp = v;
 }
 
-template <int BM, int BN, int WM, int WN, bool BATCHED>
+template <int BM, int BN, int WM, int WN, bool BATCHED, int BK, int STAGES>
 static int launch_cfg(Ctx* ctx, int flags, const GemmP& p, const GemmP* d_batch, int nb, int max_m, int max_n,
                       int tri_keep, int splitk) {
-  constexpr size_t smem = (size_t)GEMM_STAGES * (BM + BN) * LDK * sizeof(double);
+  constexpr size_t smem = (size_t)STAGES * (BM + BN) * (BK + 4) * sizeof(double);
+  static_assert(smem <= 227 * 1024, "shared memory per CTA");
   static bool attr_dev[64] = {};  // per device: the attribute belongs to the device's context
   bool& attr_set = attr_dev[ctx->device & 63];
-  auto kern = gemm_kernel<BM, BN, WM, WN, BATCHED>;
+  auto kern = gemm_kernel<BM, BN, WM, WN, BATCHED, BK, STAGES>;
   if (!attr_set) {
     EKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
@@ -367,10 +587,24 @@ static int launch_cfg(Ctx* ctx, int flags, const GemmP& p, const GemmP* d_batch,
   return 0;
 }
 
+// Tile shape by the problem shape, pipeline geometry by the k-depth each CTA actually runs through.
+template <bool BATCHED>
+static int launch_shape(Ctx* ctx, int flags, const GemmP& p, const GemmP* d_batch, int nb, int max_m, int max_n, int tri_keep,
+                        int splitk, bool deep) {
+  if (max_n <= 64)
+    return deep ? launch_cfg<128, 64, 32, 32, BATCHED, 32, 3>(ctx, flags, p, d_batch, nb, max_m, max_n, tri_keep, splitk)
+                : launch_cfg<128, 64, 32, 32, BATCHED, 16, 4>(ctx, flags, p, d_batch, nb, max_m, max_n, tri_keep, splitk);
+  if (!BATCHED && max_m <= 64)
+    return deep ? launch_cfg<64, 128, 32, 32, BATCHED, 32, 3>(ctx, flags, p, d_batch, nb, max_m, max_n, tri_keep, splitk)
+                : launch_cfg<64, 128, 32, 32, BATCHED, 16, 4>(ctx, flags, p, d_batch, nb, max_m, max_n, tri_keep, splitk);
+  return deep ? launch_cfg<128, 128, 64, 32, BATCHED, 32, 3>(ctx, flags, p, d_batch, nb, max_m, max_n, tri_keep, splitk)
+              : launch_cfg<128, 128, 64, 32, BATCHED, 16, 4>(ctx, flags, p, d_batch, nb, max_m, max_n, tri_keep, splitk);
+}
+
 int gemm(Ctx* ctx, int flags, const GemmP& p, int tri_keep, int splitk) {
   if (p.m <= 0 || p.n <= 0) return 0;
   if (splitk > 1) {
-    int nkt = cdiv(p.k, BK);
+    int nkt = cdiv(p.k, 32);
     if (splitk > nkt) splitk = nkt > 0 ? nkt : 1;
     size_t need = (size_t)splitk * p.m * p.n * sizeof(double);
     if (need > ctx->splitk_ws_bytes) {
@@ -393,12 +627,16 @@ int gemm(Ctx* ctx, int flags, const GemmP& p, int tri_keep, int splitk) {
     }
     EKB_TRY(prof_begin(ctx, PROF_GEMM, 2.0 * p.k * elems));
   }
-  if (p.n <= 64)
-    rc = launch_cfg<128, 64, 32, 32, false>(ctx, flags, p, nullptr, 1, p.m, p.n, tri_keep, splitk);
-  else if (p.m <= 64)
-    rc = launch_cfg<64, 128, 32, 32, false>(ctx, flags, p, nullptr, 1, p.m, p.n, tri_keep, splitk);
+  // k-depth per CTA (after split-K) decides the pipeline geometry: >= 32 k-tiles of 32 amortise the longer prologue
+  const bool deep = p.k / splitk >= 1024;
+  // the TMA-fed warp-specialised kernel takes the big-tile products it supports (option "gemm_bulk", default on)
+  const bool bulk_ok = ctx->gemm_bulk != 0 && splitk == 1 && !(flags & GEMM_SYMA) && p.m > 64 && p.n > 64 &&
+                       p.k % 32 == 0 && p.k >= 64 && ((((uintptr_t)p.A | (uintptr_t)p.B) & 15) == 0) &&
+                       ((p.lda | p.ldb) & 1) == 0 && (p.m % 2 == 0) && (p.n % 2 == 0);
+  if (bulk_ok)
+    rc = deep ? launch_bulk<128, 128, 64, 32, 32, 3>(ctx, flags, p, tri_keep) : launch_bulk<128, 128, 64, 32, 16, 4>(ctx, flags, p, tri_keep);
   else
-    rc = launch_cfg<128, 128, 64, 32, false>(ctx, flags, p, nullptr, 1, p.m, p.n, tri_keep, splitk);
+    rc = launch_shape<false>(ctx, flags, p, nullptr, 1, p.m, p.n, tri_keep, splitk, deep);
   if (rc) return rc;
   if (splitk > 1) {
     i64 tot = (i64)p.m * p.n;
@@ -475,13 +713,12 @@ int gemm_profile_collect(Ctx* ctx, double* seconds, double* flops, long long* la
   return 0;
 }
 
-int gemm_batched(Ctx* ctx, int flags, const GemmP* d_batch, int nb, int max_m, int max_n) {
+int gemm_batched(Ctx* ctx, int flags, const GemmP* d_batch, int nb, int max_m, int max_n, int k_hint) {
   if (nb <= 0 || max_m <= 0 || max_n <= 0) return 0;
   GemmP dummy = {};
   EKB_TRY(prof_begin(ctx, PROF_GEMM_BATCHED, 0.0));  // FLOPs after deflation are only known on the device
   int rc;
-  if (max_n <= 64) rc = launch_cfg<128, 64, 32, 32, true>(ctx, flags, dummy, d_batch, nb, max_m, max_n, -1, 1);
-  else rc = launch_cfg<128, 128, 64, 32, true>(ctx, flags, dummy, d_batch, nb, max_m, max_n, -1, 1);
+  rc = launch_shape<true>(ctx, flags, dummy, d_batch, nb, max_m, max_n, -1, 1, /*deep=*/k_hint >= 1024);
   if (rc) return rc;
   return prof_end(ctx);
 }

@@ -566,7 +566,7 @@ int stedc(Ctx* ctx, i64 n, double* d, double* e, double* w, double* Z, i64 ldz, 
     }
     dc_gemm_setup_kernel<<<cdiv(cnt, 128), 128, 0, ctx->stream>>>(nodes, cnt, d_gp, W1, ld, Qnxt, ldnxt, W2, ld, crange); EKB_COUNT_LAUNCH(ctx);
     EKB_CUDA(cudaGetLastError());
-    if (col_hi > col_lo || !top_cut) EKB_TRY(gemm_batched(ctx, 0, d_gp, 2 * cnt, maxn1, max_cols));
+    if (col_hi > col_lo || !top_cut) EKB_TRY(gemm_batched(ctx, 0, d_gp, 2 * cnt, maxn1, max_cols, /*k_hint=*/maxn1));
     dc_permute_kernel<<<dim3(maxsz, cdiv(maxsz, 256), cnt), 256, 0, ctx->stream>>>(nodes, wk, W2, ld, Qcur, ldcur, Qnxt,
                                                                                 ldnxt, plo, phi); EKB_COUNT_LAUNCH(ctx);
     EKB_CUDA(cudaGetLastError());

@@ -28,11 +28,46 @@ constexpr int QR_THREADS = 256;
 // range.  partial: 2 * G * 64 doubles.  Rout: b x b (ld b) receives R (upper triangle); tau: b.
 // In place, rows below the diagonal of column c hold v_c (unit element implicit); the upper triangle of
 // the top b x b block is left stale (fixed by fixup_extract_kernel).
+// Grid barrier for a NON-cooperative launch (bar != nullptr): a monotonically growing arrival counter in global memory.
+// The look-ahead runs this kernel on a side stream while the trailing update fills the chip; a cooperative grid is only
+// started once ALL its CTAs fit at the same time, i.e. after the update has drained (measured: no overlap at all),
+// whereas ordinary CTAs of a higher-priority stream take the SMs one by one as they fall free and wait here for the
+// rest.  Safe because nothing the running update does depends on this kernel, so every CTA does get an SM.
+__device__ __forceinline__ void sw_grid_barrier(unsigned* bar, unsigned nctas, unsigned& phase) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ++phase;
+    __threadfence();
+    atomicAdd(bar, 1u);
+    const unsigned target = phase * nctas;
+    while (*reinterpret_cast<volatile unsigned*>(bar) < target) {}
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// Gate on the main stream: holds the trailing update back until every CTA of the side-stream panel QR is resident
+// (bar[2] >= seq), so that the QR owns its few SMs BEFORE the update's thousands of CTAs flood the chip.  (Stream
+// priorities alone did not do it: measured, the QR's CTAs were only placed after the update's grid had drained.)  The
+// wait is bounded: if the QR cannot start, the update simply goes first and the QR runs after it, as without look-ahead.
+__global__ void qr_resident_gate_kernel(const unsigned* __restrict__ bar, unsigned seq) {
+  const long long t0 = clock64();
+  while (*reinterpret_cast<const volatile unsigned*>(bar + 2) < seq && clock64() - t0 < (1ll << 22)) {}
+}
+
 template <int B>
 __global__ void __launch_bounds__(QR_THREADS) panel_qr_kernel(double* __restrict__ P, i64 ld, int m,
                                                               double* __restrict__ tau, double* __restrict__ Rout,
-                                                              double* __restrict__ partial) {
+                                                              double* __restrict__ partial, unsigned* __restrict__ bar,
+                                                              unsigned seq) {
   cg::grid_group grid = cg::this_grid();
+  unsigned phase = 0;
+  if (bar && threadIdx.x == 0) {  // bar[1]: CTAs of this launch that have started; the last one opens the gate (bar[2])
+    if (atomicAdd(bar + 1, 1u) == gridDim.x - 1) {
+      *reinterpret_cast<volatile unsigned*>(bar + 2) = seq;
+      __threadfence();
+    }
+  }
   __shared__ double red[QR_THREADS / 32][B];
   __shared__ double g[B];
   __shared__ double wv[B];
@@ -141,9 +176,139 @@ __global__ void __launch_bounds__(QR_THREADS) panel_qr_kernel(double* __restrict
         partial[(size_t)(jn & 1) * G * B + blockIdx.x * B + tid] = s;
       }
     }
-    grid.sync();
+    if (bar) sw_grid_barrier(bar, (unsigned)G, phase);
+    else grid.sync();
   }
   // reflectors that do not exist (m < B): tau = 0, R rows beyond m are zero
+  if (blockIdx.x == 0 && tid < B && tid >= kr) tau[tid] = 0.0;
+}
+
+// ---- the same factorization with the panel RESIDENT IN SHARED MEMORY (round 2).
+// panel_qr_kernel walks its rows of the panel in global memory once per column: 64 passes whose loads are L2 round
+// trips (18 us per column at m = 32000: 1.15 ms per panel, 0.59 s of the n = 32768 solve, all of it with 148 - G SMs
+// idle).  Here every CTA copies its <= 352 rows (176 KB) into shared memory once, does all 64 update + dot passes there
+// (thread = (column, row slice): no shuffles, conflict-free columns with an odd leading dimension), and only the
+// per-column exchange crosses CTAs: the partial dots of the next pivot column and that pivot's ROW (whose owner
+// publishes it, since the global copy of the panel is stale until the final write-back), one software grid barrier
+// per column.  Cooperative launch for co-residency; same outputs, same operation order per element as the kernel above
+// except for the order of the partial sums.
+constexpr int QRS_MAXROWS = 352;
+template <int B>
+__global__ void __launch_bounds__(QR_THREADS, 1) panel_qr_smem_kernel(double* __restrict__ P, i64 ld, int m,
+                                                                      double* __restrict__ tau, double* __restrict__ Rout,
+                                                                      double* __restrict__ partial,
+                                                                      double* __restrict__ rowbuf /* 2 x B */,
+                                                                      unsigned* __restrict__ bar) {
+  extern __shared__ double ps[];  // ps[c * ldp + i]: column c, local row i
+  constexpr int NQ = QR_THREADS / B;
+  __shared__ double red[NQ][B];
+  __shared__ double g[B];
+  __shared__ double wv[B];
+  __shared__ double s_scal, s_tau;
+  const int G = gridDim.x, tid = threadIdx.x;
+  const int rpc = (m + G - 1) / G;
+  const int r0 = blockIdx.x * rpc, r1 = min(m, r0 + rpc);
+  const int rows = max(0, r1 - r0);
+  const int ldp = rpc | 1;
+  const int kr = min(B, m);
+  const int c = tid % B, q = tid / B;
+  const int rs = (rows + NQ - 1) / NQ;
+  const int i0 = min(rows, q * rs), i1 = min(rows, i0 + rs);
+  unsigned phase = 0;
+
+  for (int cc = 0; cc < B; ++cc)
+    for (int i = tid; i < rows; i += QR_THREADS) ps[cc * ldp + i] = P[(i64)cc * ld + r0 + i];
+  __syncthreads();
+
+  for (int j = -1; j < kr; ++j) {
+    double scal = 0.0, tj = 0.0;
+    if (j >= 0) {
+      // partial dots of column j with columns j..B-1 (rows > j), summed over the CTAs in a fixed order
+      const double* pp = partial + (size_t)(j & 1) * G * B;
+      {
+        double sacc = 0.0;
+        if (c >= j) {
+#pragma unroll 8
+          for (int t = q; t < G; t += NQ) sacc += __ldcg(pp + t * B + c);
+        }
+        red[q][c] = sacc;
+      }
+      __syncthreads();
+      if (tid < B) {
+        double sacc = 0.0;
+#pragma unroll
+        for (int t = 0; t < NQ; ++t) sacc += red[t][tid];
+        g[tid] = sacc;
+      }
+      __syncthreads();
+      const double* prow = rowbuf + (j & 1) * B;  // row j of the panel, published by its owner before the barrier
+      if (tid == 0) {
+        const double alpha = __ldcg(prow + j);
+        const double xn2 = g[j];
+        double beta, t, sc;
+        if (xn2 == 0.0) {
+          beta = alpha; t = 0.0; sc = 0.0;
+        } else {
+          beta = -copysign(sqrt(alpha * alpha + xn2), alpha);
+          t = (beta - alpha) / beta;
+          sc = 1.0 / (alpha - beta);
+        }
+        s_scal = sc; s_tau = t;
+        if (blockIdx.x == 0) { tau[j] = t; Rout[j * B + j] = beta; }
+      }
+      __syncthreads();
+      scal = s_scal; tj = s_tau;
+      if (tid < B && tid > j) {
+        const double pjc = __ldcg(prow + tid);
+        const double w = pjc + scal * g[tid];
+        wv[tid] = tj * w;
+        if (blockIdx.x == 0) Rout[tid * B + j] = pjc - tj * w;
+      }
+      // v_j: scale column j below the pivot (the reflector, stored in place)
+      for (int i = tid; i < rows; i += QR_THREADS)
+        if (r0 + i > j) ps[j * ldp + i] *= scal;
+      __syncthreads();
+    }
+    const int jn = j + 1;  // next pivot column
+    if (jn < B) {
+      // the next pivot column first (every thread of the main pass reads its UPDATED values) ...
+      if (j >= 0) {
+        const double wn = wv[jn];
+        for (int i = tid; i < rows; i += QR_THREADS)
+          if (r0 + i > j) ps[jn * ldp + i] -= wn * ps[j * ldp + i];
+        __syncthreads();
+      }
+      // ... then reflector j on the other columns, fused with the dots of column jn against columns >= jn
+      double acc = 0.0;
+      if (c >= jn) {
+        const double wc = (j >= 0 && c > jn) ? wv[c] : 0.0;
+        const double* vj = ps + (j >= 0 ? j : 0) * ldp;
+        const double* pn = ps + jn * ldp;
+        double* pc = ps + c * ldp;
+        for (int i = i0; i < i1; ++i) {
+          const int gi = r0 + i;
+          double x = pc[i];
+          if (c > jn && j >= 0 && gi > j) {
+            x -= wc * vj[i];
+            pc[i] = x;
+          }
+          if (gi > jn) acc = fma(pn[i], x, acc);
+        }
+      }
+      red[q][c] = acc;
+      __syncthreads();
+      if (jn < kr && tid < B) {
+        double sacc = 0.0;
+#pragma unroll
+        for (int t = 0; t < NQ; ++t) sacc += red[t][tid];
+        partial[(size_t)(jn & 1) * G * B + blockIdx.x * B + tid] = sacc;
+        if (jn >= r0 && jn < r1) rowbuf[(jn & 1) * B + tid] = ps[tid * ldp + (jn - r0)];  // the owner publishes row jn
+      }
+    }
+    sw_grid_barrier(bar, (unsigned)G, phase);
+  }
+  for (int cc = 0; cc < B; ++cc)
+    for (int i = tid; i < rows; i += QR_THREADS) P[(i64)cc * ld + r0 + i] = ps[cc * ldp + i];
   if (blockIdx.x == 0 && tid < B && tid >= kr) tau[tid] = 0.0;
 }
 
@@ -228,13 +393,48 @@ __global__ void pack_vw_kernel(const double* __restrict__ V, i64 ldv, const doub
   WV[(i64)(c + b) * ldp + i] = v;
 }
 
-static int launch_panel_qr(Ctx* ctx, int b, double* P, i64 ld, int m, double* tau, double* Rout, double* partial, int G) {
-  void* args[] = {(void*)&P, (void*)&ld, (void*)&m, (void*)&tau, (void*)&Rout, (void*)&partial};
+// The shared-memory-resident QR: G = ceil(m / 256) CTAs (<= one per SM), cooperative launch, software grid barrier on
+// bar[0] (zeroed here).  Returns -1 when the panel does not fit (m > 352 rows per SM): the caller then uses the
+// global-memory kernel.
+static int launch_panel_qr_smem(Ctx* ctx, int b, double* P, i64 ld, int m, double* tau, double* Rout, double* partial,
+                                double* rowbuf, unsigned* bar) {
+  int G = (m + QR_THREADS - 1) / QR_THREADS;
+  if (G > ctx->num_sms) G = ctx->num_sms;
+  const int rpc = (m + G - 1) / G;
+  if (rpc > QRS_MAXROWS) return -1;
+  const size_t smem = (size_t)(rpc | 1) * b * sizeof(double);
+  void* args[] = {(void*)&P, (void*)&ld, (void*)&m, (void*)&tau, (void*)&Rout, (void*)&partial, (void*)&rowbuf, (void*)&bar};
+  void* kern = b == 64 ? (void*)panel_qr_smem_kernel<64> : (void*)panel_qr_smem_kernel<32>;
+  static bool attr_dev[64] = {};
+  if (!attr_dev[ctx->device & 63]) {
+    EKB_CUDA(cudaFuncSetAttribute(panel_qr_smem_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (QRS_MAXROWS | 1) * 64 * (int)sizeof(double)));
+    EKB_CUDA(cudaFuncSetAttribute(panel_qr_smem_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (QRS_MAXROWS | 1) * 32 * (int)sizeof(double)));
+    attr_dev[ctx->device & 63] = true;
+  }
   EKB_TRY(prof_begin(ctx, PROF_PANEL_QR, 2.0 * m * (double)b * b));
-  if (b == 64)
+  EKB_CUDA(cudaMemsetAsync(bar, 0, sizeof(unsigned), ctx->stream));
+  EKB_CUDA(cudaLaunchCooperativeKernel(kern, dim3(G), dim3(QR_THREADS), args, smem, ctx->stream));
+  EKB_COUNT_LAUNCH(ctx);
+  return prof_end(ctx);
+}
+
+// bar == nullptr: cooperative launch (grid.sync); otherwise an ordinary launch with the software barrier on *bar.
+static int launch_panel_qr(Ctx* ctx, int b, double* P, i64 ld, int m, double* tau, double* Rout, double* partial, int G,
+                           unsigned* bar = nullptr, unsigned seq = 0) {
+  void* args[] = {(void*)&P, (void*)&ld, (void*)&m, (void*)&tau, (void*)&Rout, (void*)&partial, (void*)&bar, (void*)&seq};
+  EKB_TRY(prof_begin(ctx, PROF_PANEL_QR, 2.0 * m * (double)b * b));
+  if (bar) {
+    EKB_CUDA(cudaMemsetAsync(bar, 0, 2 * sizeof(unsigned), ctx->stream));  // arrivals, started (bar[2], the gate, only grows)
+    if (b == 64) panel_qr_kernel<64><<<G, QR_THREADS, 0, ctx->stream>>>(P, ld, m, tau, Rout, partial, bar, seq);
+    else panel_qr_kernel<32><<<G, QR_THREADS, 0, ctx->stream>>>(P, ld, m, tau, Rout, partial, bar, seq);
+    EKB_CUDA(cudaGetLastError());
+  } else if (b == 64) {
     EKB_CUDA(cudaLaunchCooperativeKernel((void*)panel_qr_kernel<64>, dim3(G), dim3(QR_THREADS), args, 0, ctx->stream));
-  else
+  } else {
     EKB_CUDA(cudaLaunchCooperativeKernel((void*)panel_qr_kernel<32>, dim3(G), dim3(QR_THREADS), args, 0, ctx->stream));
+  }
   EKB_COUNT_LAUNCH(ctx);
   return prof_end(ctx);
 }
@@ -254,7 +454,7 @@ size_t sy2sb_workspace_doubles(i64 n, int b, int num_sms) {
   i64 ldp = round_up(n, 8);
   return (size_t)ldp * b * 2      /* W0/X, (spare) */
          + (size_t)ldp * 2 * b * 2 /* VW, WV */
-         + (size_t)2 * num_sms * 64 + 8 * 64 * 64;
+         + (size_t)2 * num_sms * 64 + 8 * 64 * 64 + 8 /* grid-barrier words */ + 128 /* pivot rows of the shared-memory QR */;
 }
 
 // Work issued inside this scope goes to the context's side stream (and records its profile events there).
@@ -267,14 +467,19 @@ struct OnAuxStream {
 };
 }  // namespace
 
-// Panel look-ahead.  The Householder QR of a panel is a latency chain (one grid barrier per column, ~0.1 TFLOP/s):
-// run after the trailing update it idles the whole chip for 0.6 s of a 2.8 s reduction at n = 32768.  But panel p+1
-// only needs ITS b columns of the trailing matrix updated, so per panel
+// Panel look-ahead (option "sy2sb_lookahead", OFF by default).  Panel p+1 only needs ITS b columns of the trailing
+// matrix updated, so per panel
 //   main stream:  W_p (SYMM etc.) -> skinny update of the next panel's columns -> [event] -> rank-2b update of the rest
 //   side stream:                                             [wait] QR, band extraction, T of panel p+1 -> [event]
-// and the main stream waits for that event before the SYMM of panel p+1.  The QR grid is kept small (it is bound by
-// its barriers, not by throughput), so the big update keeps > 90 % of the SMs; the side stream has the higher priority
-// so that the QR's CTAs take the first SMs that fall free.
+// and the main stream waits for that event before the SYMM of panel p+1.  MEASURED (n = 32768, round 2,
+// profiles/r02_bench_n32768_lookahead_{on,off}.json): the reduction gets SLOWER, 2.74 s -> 4.23 s.  First as a
+// cooperative launch (a cooperative grid is only placed when all its CTAs fit at once, i.e. after the update has
+// drained), then as an ordinary launch with a software grid barrier on a high-priority stream, then with a gate kernel
+// that holds the update back until every QR CTA is resident: always ~6 ms per panel QR instead of 1.1 ms.  The QR as
+// written walks the panel in global memory and is bound by L2 round trips; beside an update that moves 2-3 TB/s those
+// round trips take several times longer, and the chain becomes the critical path.  Look-ahead needs a QR that does not
+// depend on memory latency -- which is what panel_qr_smem_kernel below is; with it the stand-alone QR is short enough
+// that the overlap is no longer worth its price.  The code path is kept for that experiment.
 int sy2sb(Ctx* ctx, i64 n, int b, double* A, i64 lda, double* AB, i64 ldab, double* T1, double* work) {
   if (n <= 0) return 0;
   const i64 ldp = round_up(n, 8);
@@ -288,6 +493,8 @@ int sy2sb(Ctx* ctx, i64 n, int b, double* A, i64 lda, double* AB, i64 ldab, doub
   double* Gm = Rout + 64 * 64;       // b*b
   double* S = Gm + 64 * 64;          // b*b
   double* TS = S + 64 * 64;          // b*b
+  unsigned* qr_bar = reinterpret_cast<unsigned*>(small + 8 * 64 * 64);
+  double* rowbuf = small + 8 * 64 * 64 + 8;
 
   bool lookahead = ctx->sy2sb_lookahead != 0 && n - b >= 4 * b;
   if (lookahead && !ctx->aux_stream) {
@@ -305,6 +512,7 @@ int sy2sb(Ctx* ctx, i64 n, int b, double* A, i64 lda, double* AB, i64 ldab, doub
       lookahead = false;
     }
 
+  if (lookahead) EKB_CUDA(cudaMemsetAsync(qr_bar, 0, 4 * sizeof(unsigned), ctx->stream));
   // QR + band extraction + T of the panel at column j (m rows below the band), on the CURRENT ctx->stream
   auto factor_panel = [&](i64 j, int p, bool side) -> int {
     const i64 m = n - j - b;
@@ -318,7 +526,11 @@ int sy2sb(Ctx* ctx, i64 n, int b, double* A, i64 lda, double* AB, i64 ldab, doub
       gs = std::min(gs, std::max(ctx->num_sms / 8, 1));
       G = std::min(G, gs);
     }
-    EKB_TRY(launch_panel_qr(ctx, b, P, lda, (int)m, tau, Rout, partial, G));
+    int qrc = -1;
+    if (!side && ctx->panel_qr_variant != 0)
+      qrc = launch_panel_qr_smem(ctx, b, P, lda, (int)m, tau, Rout, partial, rowbuf, qr_bar + 3);
+    if (qrc > 0) return qrc;
+    if (qrc < 0) EKB_TRY(launch_panel_qr(ctx, b, P, lda, (int)m, tau, Rout, partial, G, side ? qr_bar : nullptr, (unsigned)(p + 1)));
     fixup_extract_kernel<<<1, 256, 0, ctx->stream>>>(A, lda, n, j, b, Rout, AB, ldab); EKB_COUNT_LAUNCH(ctx);
     EKB_CUDA(cudaGetLastError());
     GemmP g;
@@ -376,6 +588,8 @@ int sy2sb(Ctx* ctx, i64 n, int b, double* A, i64 lda, double* AB, i64 ldab, doub
         EKB_CUDA(cudaEventRecord(ctx->aux_ev[0], ctx->stream));
       }
       factored = true;
+      qr_resident_gate_kernel<<<1, 1, 0, ctx->stream>>>(qr_bar, (unsigned)(p + 2)); EKB_COUNT_LAUNCH(ctx);
+      EKB_CUDA(cudaGetLastError());
       // 5b. ... while the rest of the trailing matrix (lower tiles + one tile diagonal of A22[b:, b:]) is updated here
       g.m = (int)(m - b); g.n = (int)(m - b); g.k = 2 * b; g.A = VW + b; g.lda = ldp; g.B = WV + b; g.ldb = ldp;
       g.C = A22 + (i64)b * lda + b; g.ldc = lda;
@@ -481,7 +695,7 @@ int sy2sb_dist(Ctx* ctx, i64 n, int b, double* A, i64 lda, double* AB, i64 ldab,
   if (!rc) rc = get(&Vloc, (size_t)round_up(nlmax, 8) * b);
   if (!rc) rc = get(&WVloc, (size_t)round_up(nlmax, 8) * 2 * b);
   if (!rc) rc = get(&msg, msg_doubles);
-  if (!rc) rc = get(&small, (size_t)2 * ctx->num_sms * 64 + 8 * 64 * 64);
+  if (!rc) rc = get(&small, (size_t)2 * ctx->num_sms * 64 + 8 * 64 * 64 + 8 + 128);
   if (!rc) rc = get(&tail, (size_t)ldp * (b + 2));
   if (rc) { cleanup(); return rc; }
   double* partial = small;
@@ -490,6 +704,8 @@ int sy2sb_dist(Ctx* ctx, i64 n, int b, double* A, i64 lda, double* AB, i64 ldab,
   double* Gm = Rout + 64 * 64;
   double* S = Gm + 64 * 64;
   double* TS = S + 64 * 64;
+  unsigned* qr_bar = reinterpret_cast<unsigned*>(TS + 64 * 64);  // grid-barrier word of the shared-memory panel QR
+  double* rowbuf = TS + 64 * 64 + 8;                             // its published pivot rows (2 x b)
   const i64 ldvl = round_up(nlmax, 8);
 
   auto body = [&]() -> int {
@@ -514,7 +730,10 @@ int sy2sb_dist(Ctx* ctx, i64 n, int b, double* A, i64 lda, double* AB, i64 ldab,
         double* Pl = Aloc + (lb * b) * ldl + (j + b);
         int G = (int)((m + QR_THREADS - 1) / QR_THREADS);
         if (G > ctx->num_sms) G = ctx->num_sms;
-        EKB_TRY(launch_panel_qr(ctx, b, Pl, ldl, (int)m, tau, Rout, partial, G));
+        int qrc = ctx->panel_qr_variant != 0
+                      ? launch_panel_qr_smem(ctx, b, Pl, ldl, (int)m, tau, Rout, partial, rowbuf, qr_bar) : -1;
+        if (qrc > 0) return qrc;
+        if (qrc < 0) EKB_TRY(launch_panel_qr(ctx, b, Pl, ldl, (int)m, tau, Rout, partial, G));
         // band columns into the message (as if AB started at column j), V made explicit in place
         fixup_extract_kernel<<<1, 256, 0, ctx->stream>>>(Aloc + (lb * b - j) * ldl, ldl, n, j, b, Rout, msgAB - j * ldab, ldab);
         EKB_COUNT_LAUNCH(ctx);

@@ -52,6 +52,12 @@ class Context:
                               " -- a CUDA device is required; there is no CPU fallback")
         self.h = h
         self.device = device
+        # EKB200_OPTIONS="key=value,...": library tuning options for experiments (ekb200_set_option), e.g. running the
+        # whole test suite with an alternative kernel selected
+        import os
+        for kv in filter(None, os.environ.get("EKB200_OPTIONS", "").split(",")):
+            k, v = kv.split("=")
+            self.set_option(k.strip(), int(v))
 
     # -- plumbing
     def call(self, name: str, *args) -> int:
