@@ -59,7 +59,7 @@ struct Ctx {
   int sb2st_rwarp = 1;                // 1: one extra warp forms the reflectors beside the updates; 0: warp 0 does
   int sb2st_cps = 0;                  // cap on resident CTAs per SM (0 = what the occupancy calculator allows)
   long long out_block = 0;            // > 0: host entry points deliver the 1 x P block-cyclic piece with this block size (layout.h)
-  int gemm_bulk = 0;                  // 1: big-tile products run on the TMA-fed warp-specialised GEMM kernel (gemm.cu)
+  int gemm_bulk = 1;                  // 1: big-tile products run on the TMA-fed warp-specialised GEMM kernel (gemm.cu)
   int panel_qr_variant = 1;           // 1: panel QR with the panel resident in shared memory; 0: the round-1 global-memory kernel
   int sy2sb_lookahead = 0;            // 1: factor panel p+1 on the side stream while the rank-2b update of panel p runs (measured: a loss, see sy2sb.cu)
   int q2_kc = 0;                      // columns of Z per CTA in apply_q2 (0 = choose; 64|80|96|112|128)

@@ -399,17 +399,24 @@ __global__ void __launch_bounds__(BULK_THREADS, 1) gemm_bulk_kernel(GemmP p, int
   if (m0 >= p.m || n0 >= p.n) return;
   if (tri_keep >= 0 && n0 - (m0 + BM - 1) >= tri_keep) return;
   const int nk = p.k / BK;
-  const bool ta = flags & GEMM_TA, tb = flags & GEMM_TB;
+  const bool ta = flags & GEMM_TA, tb = flags & GEMM_TB, syma = flags & GEMM_SYMA;
   const bool b_kmajor = !tb;
   double* sA = smem;
   double* sB = smem + STAGES * A_TILE;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int rowsA = min(BM, p.m - m0), rowsB = min(BN, p.n - n0);
+  // symmetric A (one triangle + a 128 band stored): k-tiles beyond this tile's diagonal block are read transposed
+  auto a_is_kmajor = [&](int kt) -> bool { return syma ? (kt * BK) >= m0 + BM : ta; };
 
+  // K-major operand tiles (rows of only BK doubles) are NOT worth a bulk copy each -- the copies of a warp are issued
+  // one lane at a time, 128 of them per tile took longer than the tile's DMMAs (measured: 17 TF) -- so the producer
+  // warp moves those with LDGSTS (16 bytes per lane, the same instruction count as the 8-warp kernel spends in total)
+  // and signals them with cp.async.mbarrier.arrive.noinc: one arrival per lane on top of the expect_tx arrival.
+  const bool any_km = ta || b_kmajor || syma;
   if (tid == 0) {
 #pragma unroll
     for (int st = 0; st < STAGES; ++st) {
-      mbar_init(&full_bar[st], 1);
+      mbar_init(&full_bar[st], any_km ? 33 : 1);
       mbar_init(&empty_bar[st], BULK_CONSUMER_WARPS);
     }
   }
@@ -421,27 +428,37 @@ __global__ void __launch_bounds__(BULK_THREADS, 1) gemm_bulk_kernel(GemmP p, int
 
   if (warp == BULK_CONSUMER_WARPS) {
     // ---------------- producer warp
-    const unsigned bytes = (unsigned)(rowsA + rowsB) * BK * 8u;
+    constexpr int CPR = BK / 2;        // 16-byte chunks per K-major row
+    constexpr int RPP = 32 / CPR;      // rows covered by one LDGSTS of the warp
+    const int lrow = lane / CPR, lchk = (lane % CPR) * 2;
     for (int it = 0; it < nk; ++it) {
       const int stage = it % STAGES;
       if (it >= STAGES) mbar_wait(&empty_bar[stage], (unsigned)((it / STAGES - 1) & 1));
+      const bool akm = a_is_kmajor(it);
+      const unsigned bytes = (unsigned)((akm ? 0 : rowsA) + (b_kmajor ? 0 : rowsB)) * BK * 8u;
       if (lane == 0) mbar_arrive_expect_tx(&full_bar[stage], bytes);
       __syncwarp();
       const i64 k0 = (i64)it * BK;
       double* dA = sA + stage * A_TILE;
       double* dB = sB + stage * B_TILE;
-      if (ta) {
-        for (int r = lane; r < rowsA; r += 32) bulk_g2s(dA + r * LDK, p.A + (i64)(m0 + r) * p.lda + k0, BK * 8u, &full_bar[stage]);
+      if (akm) {
+        const double* src = p.A + (i64)(m0 + lrow) * p.lda + k0 + lchk;
+        unsigned dst = smem_u32(dA + lrow * LDK + lchk);
+        for (int r = lrow; r < rowsA; r += RPP, src += (i64)RPP * p.lda, dst += RPP * LDK * 8u) cp_async16_full(dst, src);
       } else {
         for (int kk = lane; kk < BK; kk += 32)
           bulk_g2s(dA + kk * (BM + 4), p.A + (k0 + kk) * p.lda + m0, (unsigned)rowsA * 8u, &full_bar[stage]);
       }
       if (b_kmajor) {
-        for (int r = lane; r < rowsB; r += 32) bulk_g2s(dB + r * LDK, p.B + (i64)(n0 + r) * p.ldb + k0, BK * 8u, &full_bar[stage]);
+        const double* src = p.B + (i64)(n0 + lrow) * p.ldb + k0 + lchk;
+        unsigned dst = smem_u32(dB + lrow * LDK + lchk);
+        for (int r = lrow; r < rowsB; r += RPP, src += (i64)RPP * p.ldb, dst += RPP * LDK * 8u) cp_async16_full(dst, src);
       } else {
         for (int kk = lane; kk < BK; kk += 32)
           bulk_g2s(dB + kk * (BN + 4), p.B + (k0 + kk) * p.ldb + n0, (unsigned)rowsB * 8u, &full_bar[stage]);
       }
+      if (any_km)  // this lane's arrival fires when all its LDGSTS above have landed
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(&full_bar[stage])) : "memory");
     }
     return;
   }
@@ -492,14 +509,15 @@ __global__ void __launch_bounds__(BULK_THREADS, 1) gemm_bulk_kernel(GemmP p, int
     }
     beta = 0.0;
   }
-  const int a_t = ta ? (wm * WM + lq) * LDK + lr : (wm * WM + lq) + lr * (BM + 4);
+  const int a_t_km = (wm * WM + lq) * LDK + lr, a_t_mn = (wm * WM + lq) + lr * (BM + 4);
   const int b_t = b_kmajor ? (wn * WN + lq) * LDK + lr : (wn * WN + lq) + lr * (BN + 4);
   for (int it = 0; it < nk; ++it) {
     const int stage = it % STAGES;
     mbar_wait(&full_bar[stage], (unsigned)((it / STAGES) & 1));
-    const double* tA = sA + stage * A_TILE + a_t;
+    const bool akm = a_is_kmajor(it);
+    const double* tA = sA + stage * A_TILE + (akm ? a_t_km : a_t_mn);
     const double* tB = sB + stage * B_TILE + b_t;
-    if (ta) {
+    if (akm) {
       if (b_kmajor) mma_ktile<MI, NI, BM, BN, BK, true, true>(acc, tA, tB);
       else mma_ktile<MI, NI, BM, BN, BK, true, false>(acc, tA, tB);
     } else {
@@ -603,6 +621,9 @@ static int launch_shape(Ctx* ctx, int flags, const GemmP& p, const GemmP* d_batc
 
 int gemm(Ctx* ctx, int flags, const GemmP& p, int tri_keep, int splitk) {
   if (p.m <= 0 || p.n <= 0) return 0;
+  // split-K exists to fill the chip when there are few tiles; with at least one 128-row tile per SM the TMA-fed kernel
+  // (no split-K form) is the better use of them and saves the partial-sum pass
+  if (splitk > 1 && ctx->gemm_bulk != 0 && cdiv(p.m, 128) * (p.n > 64 ? cdiv(p.n, 128) : 1) >= ctx->num_sms) splitk = 1;
   if (splitk > 1) {
     int nkt = cdiv(p.k, 32);
     if (splitk > nkt) splitk = nkt > 0 ? nkt : 1;
@@ -630,11 +651,13 @@ int gemm(Ctx* ctx, int flags, const GemmP& p, int tri_keep, int splitk) {
   // k-depth per CTA (after split-K) decides the pipeline geometry: >= 32 k-tiles of 32 amortise the longer prologue
   const bool deep = p.k / splitk >= 1024;
   // the TMA-fed warp-specialised kernel takes the big-tile products it supports (option "gemm_bulk", default on)
-  const bool bulk_ok = ctx->gemm_bulk != 0 && splitk == 1 && !(flags & GEMM_SYMA) && p.m > 64 && p.n > 64 &&
-                       p.k % 32 == 0 && p.k >= 64 && ((((uintptr_t)p.A | (uintptr_t)p.B) & 15) == 0) &&
-                       ((p.lda | p.ldb) & 1) == 0 && (p.m % 2 == 0) && (p.n % 2 == 0);
-  if (bulk_ok)
+  const bool bulk_ok = ctx->gemm_bulk != 0 && splitk == 1 && p.m > 64 && p.k % 32 == 0 && p.k >= 64 &&
+                       ((((uintptr_t)p.A | (uintptr_t)p.B) & 15) == 0) && ((p.lda | p.ldb) & 1) == 0 &&
+                       (p.m % 2 == 0) && (p.n % 2 == 0);
+  if (bulk_ok && p.n > 64)
     rc = deep ? launch_bulk<128, 128, 64, 32, 32, 3>(ctx, flags, p, tri_keep) : launch_bulk<128, 128, 64, 32, 16, 4>(ctx, flags, p, tri_keep);
+  else if (bulk_ok)
+    rc = deep ? launch_bulk<128, 64, 32, 32, 32, 3>(ctx, flags, p, tri_keep) : launch_bulk<128, 64, 32, 32, 16, 4>(ctx, flags, p, tri_keep);
   else
     rc = launch_shape<false>(ctx, flags, p, nullptr, 1, p.m, p.n, tri_keep, splitk, deep);
   if (rc) return rc;
