@@ -425,11 +425,33 @@ def run_ours(args) -> None:
         return
 
     # ---- roofline of the dominant kernel family: the DMMA GEMM engine (tensor pipe, FP64)
+    # traffic: DRAM bytes of ONE launch of the family's main kernel from the committed `ncu --set full` capture (the
+    # 8192^3 product: 2 x 0.54 GB of operands + 0.54 GB of C algorithmically); null when the summary is not there
+    traffic, traffic_note = None, None
+    try:
+        rd = wr = None
+        tpath = os.path.join(ROOT, "profiles", "r02_gemm_bulk_8192_ncu.txt")
+        for ln in open(tpath):
+            w_ = ln.split()
+            if "dram__bytes_read.sum" in ln:
+                rd = float(w_[2]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[w_[3]]
+            if "dram__bytes_write.sum" in ln:
+                wr = float(w_[2]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[w_[3]]
+        if rd is not None and wr is not None:
+            traffic = rd + wr
+            traffic_note = ("dram__bytes_read + dram__bytes_write of one gemm_bulk_kernel launch, 8192^3 FP64, from "
+                            "profiles/r02_gemm_bulk_8192_ncu.txt (ncu --set full); algorithmic bytes of that launch "
+                            "1.61e9 (A, B, C once): the operands are re-read through the 126 MB L2 about 15x, at 8 % "
+                            "of the DRAM peak -- the kernel is tensor-bound (96 % pipe-active)")
+    except Exception:
+        pass
     gemm_share = gs.value / max(sec.value, 1e-30)
     roof = {
-        "bound": "tensor", "kernel": "ekb::gemm_kernel<*> (DMMA.8x8x4 engine, all tile configs)",
+        "bound": "tensor", "kernel": "ekb::gemm_bulk_kernel<*> + ekb::gemm_kernel<*> (DMMA.8x8x4 engine: TMA-fed warp-specialised kernel "
+                                    "and the LDGSTS kernel for batched / split-K / odd shapes)",
         "achieved": gf.value / max(gs.value, 1e-30) / 1e12, "peak": peak["dmma_tflops"], "unit": "TFLOP/s",
-        "frac": gf.value / max(gs.value, 1e-30) / 1e12 / peak["dmma_tflops"], "traffic": None,
+        "frac": gf.value / max(gs.value, 1e-30) / 1e12 / peak["dmma_tflops"], "traffic": traffic,
+        "traffic_note": traffic_note,
         "launches": int(gl.value), "seconds_in_kernel_per_step": gs.value / K, "share_of_step": gemm_share,
         "peak_source": "FP64 DMMA issue-rate microbenchmark run by this process (ekb200_measure_fp64_peak); "
                        "MEASURED_PEAKS.json has no FP64 figure",
