@@ -148,6 +148,11 @@ int ekb200_set_option(ekb200_ctx* h, const char* key, int64_t value) {
     ctx->out_block = value;
     return 0;
   }
+  if (!strcmp(key, "stedc_shard")) {  // shard the level-1 merges of the divide and conquer over the ranks (tuning)
+    if (value != 0 && value != 1) return -3;
+    ctx->stedc_shard = (int)value;
+    return 0;
+  }
   if (!strcmp(key, "gemm_bulk")) {  // TMA-fed warp-specialised GEMM kernel for the big-tile products (tuning)
     if (value != 0 && value != 1) return -3;
     ctx->gemm_bulk = (int)value;
@@ -563,6 +568,7 @@ static int solve_host(ekb200_ctx* h, int64_t n, int64_t nev, const double* A, in
   double *dA = nullptr, *dB = nullptr, *dZ = nullptr, *dw = nullptr;
   auto cleanup = [&]() {
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream);
     ctx_free(ctx, dA); ctx_free(ctx, dB); ctx_free(ctx, dZ); ctx_free(ctx, dw);
   };
   int rc = ctx_alloc(ctx, (void**)&dA, (size_t)ld * n * 8);
@@ -570,6 +576,7 @@ static int solve_host(ekb200_ctx* h, int64_t n, int64_t nev, const double* A, in
   if (!rc) rc = ctx_alloc(ctx, (void**)&dZ, (size_t)ld * nev * 8);
   if (!rc) rc = ctx_alloc(ctx, (void**)&dw, (size_t)(n + 8) * 8);
   if (rc) { cleanup(); return rc; }
+  HostOverlap ov;
   {
     StageTimer t(ctx, hasB ? "solve_with_general_b200:setup_matrices" : "eigen_solver_b200:setup_matrices");
     cudaError_t ce = cudaSuccess;
@@ -590,11 +597,29 @@ static int solve_host(ekb200_ctx* h, int64_t n, int64_t nev, const double* A, in
       if (ce != cudaSuccess) return 0;
       return symmetrize_from_lower(ctx, D, ld, n);
     };
-    if (cooA) rc = ekb200_coo_to_dense(h, n, cooA->nnz, cooA->ij, cooA->v, dA, ld);
-    else rc = upload(A, lda, dA);
-    if (!rc && ce == cudaSuccess && hasB) {
-      if (cooB) rc = ekb200_coo_to_dense(h, n, cooB->nnz, cooB->ij, cooB->v, dB, ld);
-      else rc = upload(B, ldb, dB);
+    // One rank, generalized, dense host inputs: B goes first (the Cholesky factorization needs it), A follows on the
+    // side stream and lands while B is being factored (0.16 s of PCIe time at n = 32768 hidden behind 0.5 s of potrf);
+    // the solver waits for ov.a_ready before it first touches A.
+    const bool a_beside = hasB && !cooA && !cooB && ctx->nranks == 1 && n >= 4096 && ctx_ensure_aux(ctx) == 0;
+    if (a_beside) {
+      rc = upload(B, ldb, dB);
+      if (!rc && ce == cudaSuccess) ce = cudaEventRecord(ctx->aux_ev[1], ctx->stream);
+      if (!rc && ce == cudaSuccess) ce = cudaStreamWaitEvent(ctx->aux_stream, ctx->aux_ev[1], 0);
+      if (!rc && ce == cudaSuccess) {
+        cudaStream_t main_stream = ctx->stream;
+        ctx->stream = ctx->aux_stream;  // upload() and its symmetrize kernel go to the side stream
+        rc = upload(A, lda, dA);
+        if (!rc && ce == cudaSuccess) ce = cudaEventRecord(ctx->aux_ev[0], ctx->stream);
+        ctx->stream = main_stream;
+        ov.a_ready = ctx->aux_ev[0];
+      }
+    } else {
+      if (cooA) rc = ekb200_coo_to_dense(h, n, cooA->nnz, cooA->ij, cooA->v, dA, ld);
+      else rc = upload(A, lda, dA);
+      if (!rc && ce == cudaSuccess && hasB) {
+        if (cooB) rc = ekb200_coo_to_dense(h, n, cooB->nnz, cooB->ij, cooB->v, dB, ld);
+        else rc = upload(B, ldb, dB);
+      }
     }
     if (ce != cudaSuccess) {
       ctx->last_cuda = ce;
@@ -607,7 +632,12 @@ static int solve_host(ekb200_ctx* h, int64_t n, int64_t nev, const double* A, in
     h->merge_flops = 0.0;
     if (hasB) {
       rc = ensure_invd(h, n);
-      if (!rc) rc = sygvd_dev(ctx, n, nev, dA, ld, dB, ld, dw, dZ, ld, h->invd, &h->merge_flops);
+      if (!(ctx->nranks > 1 && ctx->out_block > 0)) {  // the slab goes to the caller's array chunk by chunk, beside the solve
+        ov.host_Z = Z;
+        ov.ld_host_Z = ldz;
+      }
+      if (!rc) rc = sygvd_dev(ctx, n, nev, dA, ld, dB, ld, dw, dZ, ld, h->invd, &h->merge_flops, &ov);
+      if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream);  // chunk downloads (and, on errors, a pending upload)
     } else {
       rc = syevd_dev(ctx, n, nev, dA, ld, dw, dZ, ld, &h->merge_flops);
     }
@@ -637,7 +667,7 @@ static int solve_host(ekb200_ctx* h, int64_t n, int64_t nev, const double* A, in
         const i64 wdt = std::min(nb, nloc - lc);
         ce = cudaMemcpy2DAsync(Z + lc * ldz, ldz * 8, dZ + g * ld, ld * 8, n * 8, wdt, cudaMemcpyDeviceToHost, ctx->stream);
       }
-    } else if (ce == cudaSuccess && kc > 0) {
+    } else if (ce == cudaSuccess && kc > 0 && !ov.z_downloaded) {
       ce = cudaMemcpy2DAsync(Z, ldz * 8, dZ + c0 * ld, ld * 8, n * 8, kc, cudaMemcpyDeviceToHost, ctx->stream);
     }
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);

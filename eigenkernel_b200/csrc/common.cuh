@@ -59,6 +59,7 @@ struct Ctx {
   int sb2st_rwarp = 1;                // 1: one extra warp forms the reflectors beside the updates; 0: warp 0 does
   int sb2st_cps = 0;                  // cap on resident CTAs per SM (0 = what the occupancy calculator allows)
   long long out_block = 0;            // > 0: host entry points deliver the 1 x P block-cyclic piece with this block size (layout.h)
+  int stedc_shard = 1;                // P > 1: the two level-1 merges of the D&C are sharded over the ranks (0: replicated)
   int gemm_bulk = 1;                  // 1: big-tile products run on the TMA-fed warp-specialised GEMM kernel (gemm.cu)
   int panel_qr_variant = 1;           // 1: panel QR with the panel resident in shared memory; 0: the round-1 global-memory kernel
   int sy2sb_lookahead = 0;            // 1: factor panel p+1 on the side stream while the rank-2b update of panel p runs (measured: a loss, see sy2sb.cu)
@@ -187,8 +188,18 @@ int apply_q1(Ctx* ctx, i64 n, int b, double* A, i64 lda, const double* T1, i64 k
 
 // whole-solve drivers (solve.cu)
 int syevd_dev(Ctx* ctx, i64 n, i64 nev, double* A, i64 lda, double* w, double* Z, i64 ldz, double* merge_flops);
+// Transfers of the host-pointer entry points that hide behind compute (api.cu solve_host): A may still be arriving
+// on the side stream while B is factored (a_ready: waited for before A's first use), and the eigenvectors of the
+// generalized problem can leave in column chunks on the side stream while the next chunk is back-substituted.
+struct HostOverlap {
+  cudaEvent_t a_ready = nullptr;
+  double* host_Z = nullptr;   // caller's array for the rank's slab (column 0 = first column of the slab)
+  i64 ld_host_Z = 0;
+  bool z_downloaded = false;  // out: the slab has been (queued to be) downloaded on ctx->aux_stream
+};
+int ctx_ensure_aux(Ctx* ctx);  // creates ctx->aux_stream and ctx->aux_ev on first use
 int sygvd_dev(Ctx* ctx, i64 n, i64 nev, double* A, i64 lda, double* B, i64 ldb, double* w, double* Z, i64 ldz,
-              double* invd, double* merge_flops);
+              double* invd, double* merge_flops, HostOverlap* ov = nullptr);
 
 size_t stedc_workspace_bytes(i64 n);
 // Only the eigenvector columns [col_lo, col_hi) (ascending-eigenvalue positions) of the TOP merge are formed

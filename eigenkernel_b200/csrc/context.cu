@@ -78,6 +78,19 @@ int ctx_free(Ctx* ctx, void* p) {
   return 0;
 }
 
+// Side stream (higher priority) + two reusable events: panel look-ahead experiment of sy2sb, overlapped transfers of the
+// host entry points.
+int ctx_ensure_aux(Ctx* ctx) {
+  if (!ctx->aux_stream) {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);  // hi = numerically lowest = highest priority
+    EKB_CUDA(cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, hi));
+  }
+  for (auto& e : ctx->aux_ev)
+    if (!e) EKB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  return 0;
+}
+
 // Same accumulate-by-name semantics as add_event (event_logger.f90:45-64).
 void ctx_add_event(Ctx* ctx, const char* name, double seconds) {
   for (auto& e : ctx->events) {

@@ -180,8 +180,12 @@ __device__ __forceinline__ void q2_fence_proxy_async() { asm volatile("fence.pro
 // ONE cp.async.bulk (TMA, mbarrier completion) one block ahead), read with conflict-free 128-bit loads, 0.25 loads per DMMA.  Rows that leave the
 // window are stored from registers, rows that enter are prefetched into registers one step ahead.  Every
 // global element is always touched by the same thread, so program order is all the ordering the walk needs.
-template <int B, int NBS, int NW, bool AL16, int NJ>
-__global__ void __launch_bounds__(32 * NW, 1) q2_apply_kernel(const double* __restrict__ packed,
+// RING (round 2): a (NW+1)-th warp streams the block images into a ring of THREE buffers and the compute warps
+// synchronise with it only through mbarriers (full: TMA completion; empty: one arrival per compute warp), so no warp
+// ever waits for another compute warp.  Round 1 double-buffered with a __syncthreads per block: 13 % of all stall
+// samples sat behind that barrier, and the scheduler that holds a single warp (7 warps on 4 schedulers) idled at it.
+template <int B, int NBS, int NW, bool AL16, int NJ, bool RING>
+__global__ void __launch_bounds__(32 * (NW + (RING ? 1 : 0)), 1) q2_apply_kernel(const double* __restrict__ packed,
                                                              const i64* __restrict__ blk_off, i64 n, int nS,
                                                              double* __restrict__ Z, i64 ldz, i64 k) {
   using G = Q2Geom<B, NBS>;
@@ -229,15 +233,39 @@ __global__ void __launch_bounds__(32 * NW, 1) q2_apply_kernel(const double* __re
     }
   };
 
-  __shared__ unsigned long long bars[2];
+  constexpr int NBUF = RING ? 3 : 2;
+  __shared__ unsigned long long bars[NBUF], ebars[NBUF];
   constexpr unsigned IMG_BYTES = IMG * sizeof(double);
   static_assert(IMG_BYTES % 16 == 0, "bulk copies move multiples of 16 bytes");
   if (tid == 0) {
-    q2_mbar_init(&bars[0], 1);
-    q2_mbar_init(&bars[1], 1);
+#pragma unroll
+    for (int q = 0; q < NBUF; ++q) {
+      q2_mbar_init(&bars[q], 1);
+      q2_mbar_init(&ebars[q], NW);
+    }
     q2_fence_proxy_async();
   }
   __syncthreads();
+  if (RING && warp == NW) {
+    // ---- producer warp: one bulk copy per diamond block, in the order the compute warps walk them
+    if (lane == 0) {
+      int S = nS - 1;
+      while (S >= 0 && q2_num_tasks(n, B, (i64)S * NBS) == 0) --S;
+      unsigned i = 0;
+      for (; S >= 0; --S) {
+        const int ntask = q2_num_tasks(n, B, (i64)S * NBS);
+        const double* pk = packed + blk_off[S] * (i64)IMG;
+        for (int t = 0; t < ntask; ++t, pk += IMG, ++i) {
+          const unsigned st = i % NBUF;
+          if (i >= (unsigned)NBUF) q2_mbar_wait(&ebars[st], ((i / NBUF) - 1u) & 1u);
+          q2_fence_proxy_async();
+          q2_mbar_expect_tx(&bars[st], IMG_BYTES);
+          q2_bulk_g2s(sm + st * IMG, pk, IMG_BYTES, &bars[st]);
+        }
+      }
+    }
+    return;
+  }
   auto stream_image = [&](int b, const double* src) {  // one elected thread; completion lands on bars[b]
     if (tid == 0) {
       q2_fence_proxy_async();
@@ -253,8 +281,9 @@ __global__ void __launch_bounds__(32 * NW, 1) q2_apply_kernel(const double* __re
   int S = nS - 1;
   while (S >= 0 && q2_num_tasks(n, B, (i64)S * NBS) == 0) --S;
   if (S < 0) return;
-  stream_image(0, packed + blk_off[S] * (i64)IMG);
+  if (!RING) stream_image(0, packed + blk_off[S] * (i64)IMG);
   int buf = 0;
+  unsigned blk = 0;  // RING: running index of the diamond block
 
   for (; S >= 0; --S) {
     const i64 s0 = (i64)S * NBS;
@@ -276,13 +305,20 @@ __global__ void __launch_bounds__(32 * NW, 1) q2_apply_kernel(const double* __re
     for (int t = 0; t < ntask; ++t, pk += IMG) {
       const i64 W0 = s0 + (i64)t * B;
       const bool last = t + 1 >= ntask;
-      q2_mbar_wait(&bars[buf], (phase >> buf) & 1u);  // this block's images have landed (streamed one block ahead)
-      phase ^= 1u << buf;
-      __syncthreads();    // every warp is done with the other buffer
+      if (RING) {
+        buf = (int)(blk % NBUF);
+        q2_mbar_wait(&bars[buf], (blk / NBUF) & 1u);  // this block's images have landed (the producer runs ahead)
+      } else {
+        q2_mbar_wait(&bars[buf], (phase >> buf) & 1u);  // this block's images have landed (streamed one block ahead)
+        phase ^= 1u << buf;
+        __syncthreads();    // every warp is done with the other buffer
+      }
       const double* Ys = sm + buf * IMG;
       const double* Vt = Ys + G::IMG_Y;
-      if (!last) stream_image(buf ^ 1, pk + IMG);
-      else if (S > 0) stream_image(buf ^ 1, packed + blk_off[S - 1] * (i64)IMG);
+      if (!RING) {
+        if (!last) stream_image(buf ^ 1, pk + IMG);
+        else if (S > 0) stream_image(buf ^ 1, packed + blk_off[S - 1] * (i64)IMG);
+      }
       if (!last) {        // rows entering the next window of this sweep block
         const bool fast = cols_full && W0 + G::HP + B <= n;
 #pragma unroll
@@ -331,6 +367,11 @@ __global__ void __launch_bounds__(32 * NW, 1) q2_apply_kernel(const double* __re
               }
             }
       }
+      if (RING) {  // this warp is done with the images of the block: one arrival on the buffer's "empty" barrier
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(q2_smem_u32(&ebars[buf])) : "memory");
+        ++blk;
+      }
       // ---- retire the rows that leave the window, shift, take the entering rows
       {
         const bool fast = cols_full && W0 + G::HP <= n;
@@ -360,7 +401,7 @@ __global__ void __launch_bounds__(32 * NW, 1) q2_apply_kernel(const double* __re
             for (int j = 0; j < NJ; ++j) st2(W0 + 8 * r, j, fast, zacc[r][j][0], zacc[r][j][1]);
         }
       }
-      buf ^= 1;
+      if (!RING) buf ^= 1;
     }
   }
 }
@@ -392,11 +433,13 @@ template <int B, int NBS, int NW, bool AL16, int NJ = 2>
 static cudaError_t q2_apply_launch(Ctx* ctx, const double* packed, const i64* d_off, i64 n, int nS, double* Z, i64 ldz,
                                    i64 k) {
   using G = Q2Geom<B, NBS>;
-  const size_t smem = (size_t)2 * G::IMG * sizeof(double);
-  auto kern = q2_apply_kernel<B, NBS, NW, AL16, NJ>;
+  // the producer warp costs a warp's registers: 8 warps of 16 columns (250 registers each) leave no room for it
+  constexpr bool RING = !(NW == 8 && NJ == 2);
+  const size_t smem = (size_t)(RING ? 3 : 2) * G::IMG * sizeof(double);
+  auto kern = q2_apply_kernel<B, NBS, NW, AL16, NJ, RING>;
   cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (ce != cudaSuccess) return ce;
-  kern<<<cdiv(k, 8 * NJ * NW), 32 * NW, smem, ctx->stream>>>(packed, d_off, n, nS, Z, ldz, k);
+  kern<<<cdiv(k, 8 * NJ * NW), 32 * (NW + (RING ? 1 : 0)), smem, ctx->stream>>>(packed, d_off, n, nS, Z, ldz, k);
   EKB_COUNT_LAUNCH(ctx);
   return cudaGetLastError();
 }

@@ -6,6 +6,8 @@
 //   the `-n` selecting workflows (src/solver_main.f90:59-75) as "D&C on all of T, back-transform nev columns".
 // Every stage is timed with CUDA events on the context stream and recorded under the event names of
 // SURVEY.md 8(b) so the caller can replay them through add_event (src/event_logger.f90:23-65).
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace ekb {
@@ -169,7 +171,7 @@ int syevd_dev(Ctx* ctx, i64 n, i64 nev, double* A, i64 lda, double* w, double* Z
 
 // A, B full symmetric (B SPD) on the device.  B <- L (lower), A destroyed, w ascending, Z^T B Z = I.
 int sygvd_dev(Ctx* ctx, i64 n, i64 nev, double* A, i64 lda, double* B, i64 ldb, double* w, double* Z, i64 ldz,
-              double* invd, double* merge_flops) {
+              double* invd, double* merge_flops, HostOverlap* ov) {
   if (n <= 0 || nev <= 0) return 0;
   StageTimer total(ctx, "solve_with_general_b200");
   Scratch sc(ctx);
@@ -183,6 +185,7 @@ int sygvd_dev(Ctx* ctx, i64 n, i64 nev, double* A, i64 lda, double* B, i64 ldb, 
       t.stop();
       if (rc) return rc;  // > 0: order of the leading minor that is not positive definite (info(pdpotrf))
     }
+    if (ov && ov->a_ready) EKB_CUDA(cudaStreamWaitEvent(ctx->stream, ov->a_ready, 0));  // A was uploaded beside potrf
     if (ctx->reduction == 1) {
       // ELPA-style workflow (reference src/solver_elpa_eigenexa.f90:110-150): invert the factor, two multiplies.
       // Replicated on every rank (deterministic kernels: identical bits); the recovery acts on the rank's slab.
@@ -218,9 +221,25 @@ int sygvd_dev(Ctx* ctx, i64 n, i64 nev, double* A, i64 lda, double* B, i64 ldb, 
     slab_bounds(nev, ctx->nranks, 128, zb);
     const i64 c0 = zb[ctx->rank], kc = zb[ctx->rank + 1] - zb[ctx->rank];
     int rc = 0;
-    if (kc > 0)
+    if (kc > 0 && ov && ov->host_Z && !X && kc >= 2048 && ctx_ensure_aux(ctx) == 0) {
+      // host entry point: back-substitute the slab in four column chunks and send each finished chunk to the caller's
+      // array on the side stream while the next one is solved (columns are independent in L^T X = Z)
+      const i64 step = round_up((kc + 3) / 4, 128);
+      for (i64 q0 = 0; q0 < kc && !rc; q0 += step) {
+        const i64 qc = std::min(step, kc - q0);
+        double* Zq = Z + (c0 + q0) * ldz;
+        rc = trsm_lower(ctx, TRSM_LLT, n, qc, B, ldb, invd, Zq, ldz);
+        if (rc) break;
+        EKB_CUDA(cudaEventRecord(ctx->aux_ev[1], ctx->stream));
+        EKB_CUDA(cudaStreamWaitEvent(ctx->aux_stream, ctx->aux_ev[1], 0));
+        EKB_CUDA(cudaMemcpy2DAsync(ov->host_Z + q0 * ov->ld_host_Z, ov->ld_host_Z * 8, Zq, ldz * 8, n * 8, qc,
+                                   cudaMemcpyDeviceToHost, ctx->aux_stream));
+      }
+      ov->z_downloaded = rc == 0;
+    } else if (kc > 0) {
       rc = X ? trmm_lower_t(ctx, n, kc, X, ldx, Z + c0 * ldz, ldz)  // Z <- L^-T Z as a product (pdtrmm_EV)
              : trsm_lower(ctx, TRSM_LLT, n, kc, B, ldb, invd, Z + c0 * ldz, ldz);
+    }
     t.stop();
     if (rc) return rc;
   }

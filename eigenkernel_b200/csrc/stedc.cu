@@ -377,11 +377,14 @@ __global__ void __launch_bounds__(256) dc_pack_kernel(const DcNode* __restrict__
   if (g >= nd.k1 && r < n2) W1[(i64)(off + g - nd.k1) * ldw + off + n1 + r] = src[n1 + r];
 }
 
-// Root columns [crange[0], crange[1]) of the (single) top node whose sorted position falls in [col_lo, col_hi):
-// the roots are ascending in c, so the wanted ones form one contiguous range (a superset is harmless).
-__global__ void __launch_bounds__(256) dc_colrange_kernel(const DcNode* __restrict__ nodes, DcWork wk, int col_lo, int col_hi,
-                                                          int* __restrict__ crange) {
-  const DcNode nd = nodes[0];
+// Root columns [crange[2t], crange[2t+1]) of node t = blockIdx.x whose sorted position falls in [lohi[2t], lohi[2t+1])
+// (positions relative to the node): the roots are ascending in c, so the wanted ones form one contiguous range (a
+// superset is harmless).  An empty position range gives an empty column range.
+__global__ void __launch_bounds__(256) dc_colrange_kernel(const DcNode* __restrict__ nodes, DcWork wk,
+                                                          const int* __restrict__ lohi, int* __restrict__ crange) {
+  const int t = blockIdx.x;
+  const DcNode nd = nodes[t];
+  const int col_lo = lohi[2 * t], col_hi = lohi[2 * t + 1];
   __shared__ int smin, smax;
   if (threadIdx.x == 0) { smin = nd.k; smax = 0; }
   __syncthreads();
@@ -390,10 +393,10 @@ __global__ void __launch_bounds__(256) dc_colrange_kernel(const DcNode* __restri
     if (p >= col_lo && p < col_hi) { atomicMin(&smin, c); atomicMax(&smax, c + 1); }
   }
   __syncthreads();
-  if (threadIdx.x == 0) { crange[0] = smin; crange[1] = smax > smin ? smax : smin; }
+  if (threadIdx.x == 0) { crange[2 * t] = smin; crange[2 * t + 1] = smax > smin ? smax : smin; }
 }
 
-// crange != nullptr (top level of a column-restricted solve): only root columns [crange[0], crange[1]).
+// crange != nullptr (column-restricted level): node t only forms its root columns [crange[2t], crange[2t+1]).
 __global__ void dc_gemm_setup_kernel(const DcNode* __restrict__ nodes, int nnodes, GemmP* __restrict__ gp, const double* W1,
                                      i64 ldw, const double* U, i64 ldu, double* W2, i64 ldw2,
                                      const int* __restrict__ crange) {
@@ -401,8 +404,8 @@ __global__ void dc_gemm_setup_kernel(const DcNode* __restrict__ nodes, int nnode
   if (t >= nnodes) return;
   const DcNode nd = nodes[t];
   const i64 off = nd.off;
-  const i64 ca = crange ? crange[0] : 0;
-  const int ncol = crange ? crange[1] - crange[0] : nd.k;
+  const i64 ca = crange ? crange[2 * t] : 0;
+  const int ncol = crange ? crange[2 * t + 1] - crange[2 * t] : nd.k;
   GemmP a, b;
   a.m = nd.n1; a.n = ncol; a.k = nd.k1 + nd.k2;
   a.A = W1 + off * ldw + off; a.lda = ldw;
@@ -447,8 +450,9 @@ __global__ void __launch_bounds__(256) dc_rank_kernel(const DcNode* __restrict__
 // Qnew[:, pos[c]] = c < k ? W2[:, c] : Qcur[:, defl_col[c-k]]
 __global__ void __launch_bounds__(256) dc_permute_kernel(const DcNode* __restrict__ nodes, DcWork wk, const double* __restrict__ W2,
                                                          i64 ldw2, const double* __restrict__ Qcur, i64 ldq,
-                                                         double* __restrict__ Qnew, i64 ldn, int col_lo, int col_hi) {
+                                                         double* __restrict__ Qnew, i64 ldn, const int* __restrict__ lohi) {
   const DcNode nd = nodes[blockIdx.z];
+  const int col_lo = lohi ? lohi[2 * blockIdx.z] : 0, col_hi = lohi ? lohi[2 * blockIdx.z + 1] : 0x7fffffff;
   const int c = blockIdx.x;
   if (c >= nd.sz) return;
   const int off = nd.off;
@@ -535,6 +539,8 @@ int stedc(Ctx* ctx, i64 n, double* d, double* e, double* w, double* Z, i64 ldz, 
   dc_leaf_kernel<<<cdiv(nleaf, 4), 128, 0, ctx->stream>>>(d, e, n, nleaf, Dcur, Qcur, ldcur, ctx->d_info + 1); EKB_COUNT_LAUNCH(ctx);
   EKB_CUDA(cudaGetLastError());
 
+  int shard_node = -1;      // level-1 node this rank formed a slab of (-1: level 1 not sharded)
+  double shard_frac = 0.0;  // ... and the fraction of its columns
   for (int l = depth - 1; l >= 0; --l) {
     const int cnt = 1 << l;
     DcNode* nodes = d_nodes + lvl_start[l];
@@ -556,20 +562,49 @@ int stedc(Ctx* ctx, i64 n, double* d, double* e, double* w, double* Z, i64 ldz, 
     // final positions of the merged spectrum (independent of the products, so it can steer them)
     dc_rank_kernel<<<dim3(cdiv(maxsz, 256), cnt), 256, 0, ctx->stream>>>(nodes, wk, Dnxt); EKB_COUNT_LAUNCH(ctx);
     const bool top_cut = restricted && l == 0;  // only the caller's eigenvector columns of the top merge
+    // P > 1 ranks, level 1 (two merges of n/2, a quarter of all merge FLOPs, formerly replicated): rank r forms one
+    // column slab of ONE of the two nodes, then the slabs are all-gathered (full columns of the block-diagonal Q) --
+    // every rank ends up with the same bits it would have computed itself (the products are column-wise independent).
+    const bool shard = !top_cut && l == 1 && ctx->nranks >= 2 && ctx->nranks % cnt == 0 && ctx->stedc_shard != 0 &&
+                       hn[lvl_start[l]].sz >= 512;
     int* crange = nullptr;
-    int plo = 0, phi = 0x7fffffff, max_cols = maxsz;
-    if (top_cut) {
-      crange = ctx->d_info + 8;
-      plo = (int)col_lo; phi = (int)col_hi;
-      max_cols = (int)std::max<i64>(1, col_hi - col_lo);
-      dc_colrange_kernel<<<1, 256, 0, ctx->stream>>>(nodes, wk, plo, phi, crange); EKB_COUNT_LAUNCH(ctx);
+    int* lohi = nullptr;
+    int max_cols = maxsz;
+    std::vector<i64> gbounds;
+    if (top_cut || shard) {
+      crange = ctx->d_info + 8;   // 2 ints per node of the level (<= 2 nodes)
+      lohi = ctx->d_info + 16;
+      int hl[4] = {0, 0, 0, 0};
+      if (top_cut) {
+        hl[0] = (int)col_lo; hl[1] = (int)col_hi;
+        max_cols = (int)std::max<i64>(1, col_hi - col_lo);
+      } else {
+        const int rpn = ctx->nranks / cnt, mine = ctx->rank / rpn, q = ctx->rank % rpn;
+        gbounds.assign(ctx->nranks + 1, n);
+        for (int r = 0; r < ctx->nranks; ++r) {
+          const DcNode& nd = hn[lvl_start[l] + r / rpn];
+          std::vector<i64> sb;
+          slab_bounds(nd.sz, rpn, 128, sb);
+          gbounds[r] = nd.off + sb[r % rpn];
+          if (r == ctx->rank) {
+            hl[2 * mine] = (int)sb[q]; hl[2 * mine + 1] = (int)sb[q + 1];
+            max_cols = (int)std::max<i64>(1, sb[q + 1] - sb[q]);
+            shard_node = lvl_start[l] + mine;
+            shard_frac = (double)(sb[q + 1] - sb[q]) / (double)nd.sz;
+          }
+        }
+      }
+      EKB_CUDA(cudaMemcpyAsync(lohi, hl, 2 * cnt * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+      EKB_CUDA(cudaStreamSynchronize(ctx->stream));  // hl is a stack array
+      dc_colrange_kernel<<<cnt, 256, 0, ctx->stream>>>(nodes, wk, lohi, crange); EKB_COUNT_LAUNCH(ctx);
     }
     dc_gemm_setup_kernel<<<cdiv(cnt, 128), 128, 0, ctx->stream>>>(nodes, cnt, d_gp, W1, ld, Qnxt, ldnxt, W2, ld, crange); EKB_COUNT_LAUNCH(ctx);
     EKB_CUDA(cudaGetLastError());
     if (col_hi > col_lo || !top_cut) EKB_TRY(gemm_batched(ctx, 0, d_gp, 2 * cnt, maxn1, max_cols, /*k_hint=*/maxn1));
     dc_permute_kernel<<<dim3(maxsz, cdiv(maxsz, 256), cnt), 256, 0, ctx->stream>>>(nodes, wk, W2, ld, Qcur, ldcur, Qnxt,
-                                                                                ldnxt, plo, phi); EKB_COUNT_LAUNCH(ctx);
+                                                                                ldnxt, lohi); EKB_COUNT_LAUNCH(ctx);
     EKB_CUDA(cudaGetLastError());
+    if (shard) EKB_TRY(comm_allgather_cols(ctx, Qnxt, ldnxt, gbounds));
     std::swap(Qcur, Qnxt);
     std::swap(ldcur, ldnxt);
     std::swap(Dcur, Dnxt);
@@ -589,6 +624,8 @@ int stedc(Ctx* ctx, i64 n, double* d, double* e, double* w, double* Z, i64 ldz, 
       const DcNode& nd = hn[q];
       double cols = nd.k;
       if (restricted && (int)q == lvl_start[0]) cols = ctx->h_info[9] - ctx->h_info[8];
+      if (shard_node >= 0 && depth >= 2 && (int)q >= lvl_start[1] && (int)q < lvl_start[1] + 2)
+        cols = (int)q == shard_node ? nd.k * shard_frac : 0.0;  // this rank's share of the sharded level (estimate)
       fl += 2.0 * cols * ((double)nd.n1 * (nd.k1 + nd.k2) + (double)(nd.sz - nd.n1) * (nd.k2 + nd.k3));
     }
     *flops_out = fl;

@@ -497,21 +497,10 @@ int sy2sb(Ctx* ctx, i64 n, int b, double* A, i64 lda, double* AB, i64 ldab, doub
   double* rowbuf = small + 8 * 64 * 64 + 8;
 
   bool lookahead = ctx->sy2sb_lookahead != 0 && n - b >= 4 * b;
-  if (lookahead && !ctx->aux_stream) {
-    int lo = 0, hi = 0;
-    cudaDeviceGetStreamPriorityRange(&lo, &hi);  // hi = numerically lowest = highest priority
-    if (cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, hi) != cudaSuccess) {
-      cudaGetLastError();
-      ctx->aux_stream = nullptr;
-      lookahead = false;
-    }
+  if (lookahead && ctx_ensure_aux(ctx) != 0) {
+    cudaGetLastError();
+    lookahead = false;
   }
-  for (auto& e : ctx->aux_ev)
-    if (lookahead && !e && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) {
-      cudaGetLastError();
-      lookahead = false;
-    }
-
   if (lookahead) EKB_CUDA(cudaMemsetAsync(qr_bar, 0, 4 * sizeof(unsigned), ctx->stream));
   // QR + band extraction + T of the panel at column j (m rows below the band), on the CURRENT ctx->stream
   auto factor_panel = [&](i64 j, int p, bool side) -> int {
