@@ -351,7 +351,8 @@ gemm_kernel(GemmP p0, const GemmP* __restrict__ batch, int flags, int tri_keep, 
 // Operand tiles land in the SAME padded layouts (one copy per k-contiguous row of a K-major tile, or per k-row of an
 // MN-major one: the destination of a 1-D bulk copy is free, a tensor-map box would land dense and conflict 4-way).
 // Partial tiles: rows beyond the matrix are never copied and stay at the zeros written once before the first copy.
-// Used for non-batched, non-split, non-symmetric products with 16-byte aligned operands and k a multiple of BK.
+// Serves plain, symmetric-A and batched products of any offset and size (the producer picks its copy path per tile and
+// zero-fills a k tail); split-K calls and products with m <= 64 stay on the LDGSTS kernel.
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -384,9 +385,12 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
 constexpr int BULK_CONSUMER_WARPS = 8;
 constexpr int BULK_THREADS = 32 * (BULK_CONSUMER_WARPS + 1);
 
-template <int BM, int BN, int WM, int WN, int BK, int STAGES>
-__global__ void __launch_bounds__(BULK_THREADS, 1) gemm_bulk_kernel(GemmP p, int flags, int tri_keep) {
+template <int BM, int BN, int WM, int WN, int BK, int STAGES, bool BATCHED>
+__global__ void __launch_bounds__(BULK_THREADS, 1) gemm_bulk_kernel(GemmP p0, const GemmP* __restrict__ batch, int flags,
+                                                                    int tri_keep) {
   extern __shared__ __align__(16) double smem[];
+  GemmP p = p0;
+  if (BATCHED) p = batch[blockIdx.z];
   constexpr int LDK = BK + 4;
   constexpr int A_TILE = BM * LDK;  // >= BK*(BM+4)
   constexpr int B_TILE = BN * LDK;
@@ -398,7 +402,7 @@ __global__ void __launch_bounds__(BULK_THREADS, 1) gemm_bulk_kernel(GemmP p, int
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   if (m0 >= p.m || n0 >= p.n) return;
   if (tri_keep >= 0 && n0 - (m0 + BM - 1) >= tri_keep) return;
-  const int nk = p.k / BK;
+  const int nk = (p.k + BK - 1) / BK;  // a last partial k-tile is zero-filled by the producer
   const bool ta = flags & GEMM_TA, tb = flags & GEMM_TB, syma = flags & GEMM_SYMA;
   const bool b_kmajor = !tb;
   double* sA = smem;
@@ -412,11 +416,11 @@ __global__ void __launch_bounds__(BULK_THREADS, 1) gemm_bulk_kernel(GemmP p, int
   // one lane at a time, 128 of them per tile took longer than the tile's DMMAs (measured: 17 TF) -- so the producer
   // warp moves those with LDGSTS (16 bytes per lane, the same instruction count as the 8-warp kernel spends in total)
   // and signals them with cp.async.mbarrier.arrive.noinc: one arrival per lane on top of the expect_tx arrival.
-  const bool any_km = ta || b_kmajor || syma;
+  // (Every lane of the producer arrives once per stage, whether or not it issued LDGSTS copies: 1 + 32 arrivals.)
   if (tid == 0) {
 #pragma unroll
     for (int st = 0; st < STAGES; ++st) {
-      mbar_init(&full_bar[st], any_km ? 33 : 1);
+      mbar_init(&full_bar[st], 33);
       mbar_init(&empty_bar[st], BULK_CONSUMER_WARPS);
     }
   }
@@ -428,37 +432,70 @@ __global__ void __launch_bounds__(BULK_THREADS, 1) gemm_bulk_kernel(GemmP p, int
 
   if (warp == BULK_CONSUMER_WARPS) {
     // ---------------- producer warp
+    // Copy paths per operand tile, chosen per CTA (all fill the same padded layouts):
+    //   MN-major, 16-byte aligned, even row count : one bulk copy (TMA) per k-row               [the fast path]
+    //   K-major, 16-byte aligned                  : LDGSTS.128, zero-filled past the end of k
+    //   anything else (odd offsets / sizes of the D&C merge products, k tails of MN-major tiles): LDGSTS.64 with
+    //   zero fill, still from this one warp.
     constexpr int CPR = BK / 2;        // 16-byte chunks per K-major row
-    constexpr int RPP = 32 / CPR;      // rows covered by one LDGSTS of the warp
+    constexpr int RPP = 32 / CPR;      // rows covered by one LDGSTS.128 of the warp
     const int lrow = lane / CPR, lchk = (lane % CPR) * 2;
+    const bool a_al = (((uintptr_t)p.A & 15) == 0) && ((p.lda & 1) == 0);
+    const bool b_al = (((uintptr_t)p.B & 15) == 0) && ((p.ldb & 1) == 0);
+    // one operand tile; base = element (row 0 of the tile, k = 0), ld = its leading dimension
+    auto fill = [&](double* dst, const double* base, i64 ld, bool kmajor, bool al, int rows, int BMN, i64 k0, int kvalid,
+                    unsigned long long* bar) -> unsigned {
+      unsigned tx = 0;
+      if (kmajor) {
+        if (al) {
+          const double* src = base + (i64)lrow * ld + k0 + lchk;
+          unsigned d32 = smem_u32(dst + lrow * LDK + lchk);
+          const int nb = max(0, min(16, (kvalid - lchk) * 8));
+          for (int r = lrow; r < rows; r += RPP, src += (i64)RPP * ld, d32 += RPP * LDK * 8u) {
+            if (nb == 16) cp_async16_full(d32, src);
+            else asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d32), "l"(nb > 0 ? src : base), "r"(nb) : "memory");
+          }
+        } else {
+          for (int e = lane; e < rows * BK; e += 32) {
+            const int r = e / BK, kk = e % BK;
+            cp_async8(dst + r * LDK + kk, kk < kvalid ? base + (i64)r * ld + k0 + kk : base, kk < kvalid ? 8 : 0);
+          }
+        }
+      } else {
+        const bool bulk = al && (rows % 2 == 0);
+        if (bulk) {
+          for (int kk = lane; kk < kvalid; kk += 32) bulk_g2s(dst + kk * (BMN + 4), base + (k0 + kk) * ld, (unsigned)rows * 8u, bar);
+          tx = (unsigned)rows * (unsigned)kvalid * 8u;
+        }
+        // rows of k past the end (zero fill), or the whole tile when it cannot go by bulk copies
+        for (int kk = bulk ? kvalid : 0; kk < BK; ++kk)
+          for (int mm = lane; mm < rows; mm += 32)
+            cp_async8(dst + kk * (BMN + 4) + mm, kk < kvalid ? base + (k0 + kk) * ld + mm : base, kk < kvalid ? 8 : 0);
+      }
+      return tx;
+    };
     for (int it = 0; it < nk; ++it) {
       const int stage = it % STAGES;
-      if (it >= STAGES) mbar_wait(&empty_bar[stage], (unsigned)((it / STAGES - 1) & 1));
+      if (it >= STAGES) {
+        mbar_wait(&empty_bar[stage], (unsigned)((it / STAGES - 1) & 1));
+        // the buffer was read (and possibly zero-filled) through the generic proxy; bulk copies write it through the async one
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+      }
       const bool akm = a_is_kmajor(it);
-      const unsigned bytes = (unsigned)((akm ? 0 : rowsA) + (b_kmajor ? 0 : rowsB)) * BK * 8u;
+      const i64 k0 = (i64)it * BK;
+      const int kvalid = (int)min((i64)BK, (i64)p.k - k0);
+      // expect_tx must be posted with the byte count of the bulk copies of this stage (computed as fill does)
+      const bool a_bulk = !akm && a_al && (rowsA % 2 == 0), b_bulk = !b_kmajor && b_al && (rowsB % 2 == 0);
+      const unsigned bytes = (a_bulk ? (unsigned)rowsA : 0u) * kvalid * 8u + (b_bulk ? (unsigned)rowsB : 0u) * kvalid * 8u;
       if (lane == 0) mbar_arrive_expect_tx(&full_bar[stage], bytes);
       __syncwarp();
-      const i64 k0 = (i64)it * BK;
       double* dA = sA + stage * A_TILE;
       double* dB = sB + stage * B_TILE;
-      if (akm) {
-        const double* src = p.A + (i64)(m0 + lrow) * p.lda + k0 + lchk;
-        unsigned dst = smem_u32(dA + lrow * LDK + lchk);
-        for (int r = lrow; r < rowsA; r += RPP, src += (i64)RPP * p.lda, dst += RPP * LDK * 8u) cp_async16_full(dst, src);
-      } else {
-        for (int kk = lane; kk < BK; kk += 32)
-          bulk_g2s(dA + kk * (BM + 4), p.A + (k0 + kk) * p.lda + m0, (unsigned)rowsA * 8u, &full_bar[stage]);
-      }
-      if (b_kmajor) {
-        const double* src = p.B + (i64)(n0 + lrow) * p.ldb + k0 + lchk;
-        unsigned dst = smem_u32(dB + lrow * LDK + lchk);
-        for (int r = lrow; r < rowsB; r += RPP, src += (i64)RPP * p.ldb, dst += RPP * LDK * 8u) cp_async16_full(dst, src);
-      } else {
-        for (int kk = lane; kk < BK; kk += 32)
-          bulk_g2s(dB + kk * (BN + 4), p.B + (k0 + kk) * p.ldb + n0, (unsigned)rowsB * 8u, &full_bar[stage]);
-      }
-      if (any_km)  // this lane's arrival fires when all its LDGSTS above have landed
-        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(&full_bar[stage])) : "memory");
+      // K-major A is "rows of op(A)^T": element (m, k) at A[(m0 + m) * lda + k]; MN-major: A[k * lda + m0 + m]
+      fill(dA, akm ? p.A + (i64)m0 * p.lda : p.A + m0, p.lda, akm, a_al, rowsA, BM, k0, kvalid, &full_bar[stage]);
+      fill(dB, b_kmajor ? p.B + (i64)n0 * p.ldb : p.B + n0, p.ldb, b_kmajor, b_al, rowsB, BN, k0, kvalid, &full_bar[stage]);
+      // this lane's arrival fires when all its LDGSTS above have landed
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(&full_bar[stage])) : "memory");
     }
     return;
   }
@@ -557,18 +594,19 @@ __global__ void __launch_bounds__(BULK_THREADS, 1) gemm_bulk_kernel(GemmP p, int
   }
 }
 
-template <int BM, int BN, int WM, int WN, int BK, int STAGES>
-static int launch_bulk(Ctx* ctx, int flags, const GemmP& p, int tri_keep) {
+template <int BM, int BN, int WM, int WN, int BK, int STAGES, bool BATCHED = false>
+static int launch_bulk(Ctx* ctx, int flags, const GemmP& p, int tri_keep, const GemmP* d_batch = nullptr, int nb = 1,
+                       int max_m = 0, int max_n = 0) {
   constexpr size_t smem = (size_t)STAGES * (BM + BN) * (BK + 4) * sizeof(double);
   static bool attr_dev[64] = {};
   bool& attr_set = attr_dev[ctx->device & 63];
-  auto kern = gemm_bulk_kernel<BM, BN, WM, WN, BK, STAGES>;
+  auto kern = gemm_bulk_kernel<BM, BN, WM, WN, BK, STAGES, BATCHED>;
   if (!attr_set) {
     EKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  dim3 grid(cdiv(p.m, BM), cdiv(p.n, BN), 1);
-  kern<<<grid, BULK_THREADS, smem, ctx->stream>>>(p, flags, tri_keep); EKB_COUNT_LAUNCH(ctx);
+  dim3 grid(cdiv(BATCHED ? max_m : p.m, BM), cdiv(BATCHED ? max_n : p.n, BN), BATCHED ? nb : 1);
+  kern<<<grid, BULK_THREADS, smem, ctx->stream>>>(p, d_batch, flags, tri_keep); EKB_COUNT_LAUNCH(ctx);
   EKB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -651,9 +689,7 @@ int gemm(Ctx* ctx, int flags, const GemmP& p, int tri_keep, int splitk) {
   // k-depth per CTA (after split-K) decides the pipeline geometry: >= 32 k-tiles of 32 amortise the longer prologue
   const bool deep = p.k / splitk >= 1024;
   // the TMA-fed warp-specialised kernel takes the big-tile products it supports (option "gemm_bulk", default on)
-  const bool bulk_ok = ctx->gemm_bulk != 0 && splitk == 1 && p.m > 64 && p.k % 32 == 0 && p.k >= 64 &&
-                       ((((uintptr_t)p.A | (uintptr_t)p.B) & 15) == 0) && ((p.lda | p.ldb) & 1) == 0 &&
-                       (p.m % 2 == 0) && (p.n % 2 == 0);
+  const bool bulk_ok = ctx->gemm_bulk != 0 && splitk == 1 && p.m > 64 && p.k >= 64;
   if (bulk_ok && p.n > 64)
     rc = deep ? launch_bulk<128, 128, 64, 32, 32, 3>(ctx, flags, p, tri_keep) : launch_bulk<128, 128, 64, 32, 16, 4>(ctx, flags, p, tri_keep);
   else if (bulk_ok)
@@ -741,7 +777,18 @@ int gemm_batched(Ctx* ctx, int flags, const GemmP* d_batch, int nb, int max_m, i
   GemmP dummy = {};
   EKB_TRY(prof_begin(ctx, PROF_GEMM_BATCHED, 0.0));  // FLOPs after deflation are only known on the device
   int rc;
-  rc = launch_shape<true>(ctx, flags, dummy, d_batch, nb, max_m, max_n, -1, 1, /*deep=*/k_hint >= 1024);
+  const bool deep = k_hint >= 1024;
+  if (ctx->gemm_bulk != 0 && max_m > 64 && k_hint >= 64 && !(flags & GEMM_SYMA)) {
+    // the D&C merge products: any offset, any size -- the producer warp picks its copy path per tile
+    if (max_n > 64)
+      rc = deep ? launch_bulk<128, 128, 64, 32, 32, 3, true>(ctx, flags, dummy, -1, d_batch, nb, max_m, max_n)
+                : launch_bulk<128, 128, 64, 32, 16, 4, true>(ctx, flags, dummy, -1, d_batch, nb, max_m, max_n);
+    else
+      rc = deep ? launch_bulk<128, 64, 32, 32, 32, 3, true>(ctx, flags, dummy, -1, d_batch, nb, max_m, max_n)
+                : launch_bulk<128, 64, 32, 32, 16, 4, true>(ctx, flags, dummy, -1, d_batch, nb, max_m, max_n);
+  } else {
+    rc = launch_shape<true>(ctx, flags, dummy, d_batch, nb, max_m, max_n, -1, 1, deep);
+  }
   if (rc) return rc;
   return prof_end(ctx);
 }
