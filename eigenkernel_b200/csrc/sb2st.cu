@@ -382,10 +382,10 @@ constexpr int SB2ST_TRACE_TASKS = 4096, SB2ST_TRACE_PTS = 8, SB2ST_TRACE_CTA = 5
 // divisions: the longest scalar chain of a task) runs BESIDE the rank-1/2 updates of the compute warps instead of
 // after warp 0's share of them.
 template <int B, int NW, bool RW, bool TRACE>
-// 112 registers per thread: two CTAs of 9 warps fit on an SM (the kernel needs ~168 unconstrained; at 112 ptxas
-// spills 48 bytes).  At n = 32768 the pipeline wants ~260 sweeps in flight; with one CTA per SM the first 40 % of the
-// sweeps were limited by the 148 resident CTAs.
-__global__ void __maxnreg__(112)
+// (Tried: __maxnreg__(112) so that two 9-warp CTAs fit per SM -- at n = 32768 the pipeline wants ~260 sweeps in flight
+// and one CTA per SM limits the first 40 % of the sweeps to 148.  Measured 0.460 s against 0.451 s: the two CTAs slow
+// each other down by what the extra residency gains.  One CTA per SM with the registers it wants stays.)
+__global__ void __launch_bounds__(32 * (NW + (RW ? 1 : 0)), ((NW <= 8 && !RW) ? 2 : 1))
 sb2st_reg_kernel(double* __restrict__ AB, i64 ldab, i64 n, double* __restrict__ V2, i64 ldv, double* __restrict__ TAU2,
                  int ldtau, int* __restrict__ prog, long long* __restrict__ trace) {
   constexpr int RH = B / 32;   // rows per lane

@@ -120,6 +120,27 @@ def _coo_ptrs(m: SparseMat):
     return ij, v
 
 
+def interpret_info(info: int, n: int, n_vec: int, generalized: bool) -> None:
+    """Status code of a whole-solve entry point -> the reference's reporting (generalized_to_standard.f90:25-30,
+    solver_scalapack_select.f90:61-67).  The routine name follows the RANGE of the code (include/ekb200.h), not the
+    kind of problem: 1..n = info(pdpotrf); FAIL_STEDC + k = info(pdstedc); WARN_STEIN + k is only a warning (k
+    eigenvectors did not converge in inverse iteration; the results are complete), like pdsyevx's IFAIL report."""
+    if WARN_STEIN < info < FAIL_STEDC:
+        print(f"[Warning] eigen_solver_b200_select: inverse iteration did not converge for {info - WARN_STEIN} "
+              f"of {n_vec} requested eigenvectors")
+        return
+    if info == 0:
+        return
+    if FAIL_STEDC < info < 1000000:
+        routine, info = "pdstedc", info - FAIL_STEDC
+    elif generalized and 0 < info <= n:
+        routine = "pdpotrf"
+    else:
+        routine = "ekb200_sygvd_coo"
+    print(f"info({routine}): {info}")
+    raise TerminateError(f"eigen_solver: {routine} failed", info)
+
+
 def eigen_solver(arg: Argument, matrix_A: SparseMat, matrix_B: SparseMat | None = None, *,
                  logger: EventLogger | None = None, ctx: Context | None = None, device: int = 0):
     """solver_main.f90:22-100 for the b200 cases.  Returns (eigenpairs, proc).
@@ -163,21 +184,7 @@ def eigen_solver(arg: Argument, matrix_A: SparseMat, matrix_B: SparseMat | None 
                     logger.add_event(name, 0.0, to_print=False)
                 logger.add_event(name, sec)
             logger.add_event("eigen_solver_b200:wall", wall)
-        if WARN_STEIN < info < FAIL_STEDC:
-            # pdsyevx's IFAIL report (solver_scalapack_select.f90:61-67): a warning, the results are complete
-            print(f"[Warning] eigen_solver_b200_select: inverse iteration did not converge for {info - WARN_STEIN} "
-                  f"of {n_vec} requested eigenvectors")
-            info = 0
-        if info != 0:
-            # the routine name follows the RANGE of the code (include/ekb200.h), not the kind of problem
-            if FAIL_STEDC < info < 1000000:
-                routine, info = "pdstedc", info - FAIL_STEDC
-            elif generalized and 0 < info <= n:
-                routine = "pdpotrf"
-            else:
-                routine = "ekb200_sygvd_coo"
-            print(f"info({routine}): {info}")
-            raise TerminateError(f"eigen_solver: {routine} failed", info)
+        interpret_info(info, n, n_vec, generalized)
     finally:
         if own:
             ctx.close()

@@ -131,3 +131,28 @@ def test_built_library_carries_the_blackwell_fp64_path():
     assert sass.count("DMMA.8x8x4") > 1000
     assert sass.count("LDGSTS") > 100
     assert sass.count("UBLKCP") > 0 and sass.count("SYNCS.ARRIVE.TRANS") > 0
+
+
+def test_solver_status_codes_are_reported_by_range(capsys):
+    """include/ekb200.h: 1..n = info(pdpotrf) (generalized_to_standard.f90:25-30); EKB200_FAIL_STEDC + k =
+    info(pdstedc); EKB200_WARN_STEIN + k is a warning only -- the reference reports pdsyevx's IFAIL and carries on
+    (solver_scalapack_select.f90:61-67)."""
+    from eigenkernel_b200 import solver
+    from eigenkernel_b200.app_io import TerminateError
+
+    solver.interpret_info(0, 100, 100, True)
+    solver.interpret_info(solver.WARN_STEIN + 3, 100, 40, False)          # no exception
+    assert "did not converge for 3 of 40" in capsys.readouterr().out
+    with pytest.raises(TerminateError) as e:
+        solver.interpret_info(57, 100, 100, True)
+    assert e.value.code == 57 and "info(pdpotrf): 57" in capsys.readouterr().out
+    with pytest.raises(TerminateError) as e:
+        solver.interpret_info(solver.FAIL_STEDC + 2, 100, 100, True)
+    assert e.value.code == 2 and "info(pdstedc): 2" in capsys.readouterr().out
+    with pytest.raises(TerminateError) as e:
+        solver.interpret_info(57, 100, 100, False)                        # a standard solve has no Cholesky step
+    assert "info(ekb200_sygvd_coo): 57" in capsys.readouterr().out
+    with pytest.raises(TerminateError):
+        solver.interpret_info(1000001, 100, 100, True)
+    hdr = open(os.path.join(ROOT, "include", "ekb200.h")).read()
+    assert f"#define EKB200_WARN_STEIN {solver.WARN_STEIN}" in hdr and f"#define EKB200_FAIL_STEDC {solver.FAIL_STEDC}" in hdr
