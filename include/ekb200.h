@@ -43,8 +43,10 @@ int ekb200_set_option(ekb200_ctx* ctx, const char* key, int64_t value); /* "band
                                                                            L (-s general_b200inv; solver_elpa_eigenexa.f90:110-150);
                                                                            "out_block" = NB of the caller's block-cyclic eigenvector
                                                                            descriptor (see ekb200_comm_local_cols; 0 = column slabs);
-                                                                           tuning: "sb2st_variant", "sb2st_warps", "sb2st_rwarp",
-                                                                           "sb2st_cps", "q2_kc" */
+                                                                           tuning / experiments (defaults are the measured best):
+                                                                           "sb2st_variant", "sb2st_warps", "sb2st_rwarp", "sb2st_cps",
+                                                                           "panel_qr_variant", "sy2sb_lookahead", "gemm_bulk",
+                                                                           "stedc_shard", "q2_kc" */
 int ekb200_version(void);
 int ekb200_device_count(void); /* visible CUDA devices (0 when there is none); a rank uses device = local rank */
 
