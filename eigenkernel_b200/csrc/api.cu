@@ -153,6 +153,11 @@ int ekb200_set_option(ekb200_ctx* h, const char* key, int64_t value) {
     ctx->stedc_shard = (int)value;
     return 0;
   }
+  if (!strcmp(key, "gemm_autosplit")) {  // split-K factor of TMA-fed products chosen by the round-count model (tuning)
+    if (value != 0 && value != 1) return -3;
+    ctx->gemm_autosplit = (int)value;
+    return 0;
+  }
   if (!strcmp(key, "gemm_bulk")) {  // TMA-fed warp-specialised GEMM kernel for the big-tile products (tuning)
     if (value != 0 && value != 1) return -3;
     ctx->gemm_bulk = (int)value;

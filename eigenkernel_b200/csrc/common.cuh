@@ -48,6 +48,8 @@ struct Ctx {
   // scratch
   double* splitk_ws = nullptr;        // split-K partial sums
   size_t splitk_ws_bytes = 0;
+  double* splitk_ws_aux = nullptr;    // the same for work issued on aux_stream (swapped in by OnAuxStream, sy2sb.cu)
+  size_t splitk_ws_aux_bytes = 0;
   int* d_info = nullptr;              // device-side info word(s)
   int* h_info = nullptr;              // pinned mirror
   // options
@@ -60,6 +62,7 @@ struct Ctx {
   int sb2st_cps = 0;                  // cap on resident CTAs per SM (0 = what the occupancy calculator allows)
   long long out_block = 0;            // > 0: host entry points deliver the 1 x P block-cyclic piece with this block size (layout.h)
   int stedc_shard = 1;                // P > 1: the two level-1 merges of the D&C are sharded over the ranks (0: replicated)
+  int gemm_autosplit = 1;             // 1: products on the TMA-fed kernel choose their split-K factor by the round-count model (gemm.cu)
   int gemm_bulk = 1;                  // 1: big-tile products run on the TMA-fed warp-specialised GEMM kernel (gemm.cu)
   int panel_qr_variant = 1;           // 1: panel QR with the panel resident in shared memory; 0: the round-1 global-memory kernel
   int sy2sb_lookahead = 0;            // 1: factor panel p+1 on the side stream while the rank-2b update of panel p runs (measured: a loss, see sy2sb.cu)

@@ -387,7 +387,7 @@ constexpr int BULK_THREADS = 32 * (BULK_CONSUMER_WARPS + 1);
 
 template <int BM, int BN, int WM, int WN, int BK, int STAGES, bool BATCHED>
 __global__ void __launch_bounds__(BULK_THREADS, 1) gemm_bulk_kernel(GemmP p0, const GemmP* __restrict__ batch, int flags,
-                                                                    int tri_keep) {
+                                                                    int tri_keep, int splitk, double* __restrict__ ws) {
   extern __shared__ __align__(16) double smem[];
   GemmP p = p0;
   if (BATCHED) p = batch[blockIdx.z];
@@ -402,7 +402,19 @@ __global__ void __launch_bounds__(BULK_THREADS, 1) gemm_bulk_kernel(GemmP p0, co
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   if (m0 >= p.m || n0 >= p.n) return;
   if (tri_keep >= 0 && n0 - (m0 + BM - 1) >= tri_keep) return;
-  const int nk = (p.k + BK - 1) / BK;  // a last partial k-tile is zero-filled by the producer
+  // k-tiles [kt0, kt0 + nk) of this CTA (a last partial k-tile is zero-filled by the producer); with split-K
+  // (blockIdx.z = the split) the raw partial product goes to slice z of the workspace and splitk_reduce_kernel
+  // applies alpha and beta
+  int kt0 = 0, nk = (p.k + BK - 1) / BK;
+  if (!BATCHED && splitk > 1) {
+    const int per = (nk + splitk - 1) / splitk;
+    kt0 = blockIdx.z * per;
+    nk = max(0, min(nk, kt0 + per) - kt0);
+    p.C = ws + (i64)blockIdx.z * p.m * p.n;
+    p.ldc = p.m;
+    p.alpha = 1.0;
+    p.beta = 0.0;
+  }
   const bool ta = flags & GEMM_TA, tb = flags & GEMM_TB, syma = flags & GEMM_SYMA;
   const bool b_kmajor = !tb;
   double* sA = smem;
@@ -481,8 +493,8 @@ __global__ void __launch_bounds__(BULK_THREADS, 1) gemm_bulk_kernel(GemmP p0, co
         // the buffer was read (and possibly zero-filled) through the generic proxy; bulk copies write it through the async one
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
       }
-      const bool akm = a_is_kmajor(it);
-      const i64 k0 = (i64)it * BK;
+      const bool akm = a_is_kmajor(kt0 + it);
+      const i64 k0 = (i64)(kt0 + it) * BK;
       const int kvalid = (int)min((i64)BK, (i64)p.k - k0);
       // expect_tx must be posted with the byte count of the bulk copies of this stage (computed as fill does)
       const bool a_bulk = !akm && a_al && (rowsA % 2 == 0), b_bulk = !b_kmajor && b_al && (rowsB % 2 == 0);
@@ -551,7 +563,7 @@ __global__ void __launch_bounds__(BULK_THREADS, 1) gemm_bulk_kernel(GemmP p0, co
   for (int it = 0; it < nk; ++it) {
     const int stage = it % STAGES;
     mbar_wait(&full_bar[stage], (unsigned)((it / STAGES) & 1));
-    const bool akm = a_is_kmajor(it);
+    const bool akm = a_is_kmajor(kt0 + it);
     const double* tA = sA + stage * A_TILE + (akm ? a_t_km : a_t_mn);
     const double* tB = sB + stage * B_TILE + b_t;
     if (akm) {
@@ -596,7 +608,7 @@ __global__ void __launch_bounds__(BULK_THREADS, 1) gemm_bulk_kernel(GemmP p0, co
 
 template <int BM, int BN, int WM, int WN, int BK, int STAGES, bool BATCHED = false>
 static int launch_bulk(Ctx* ctx, int flags, const GemmP& p, int tri_keep, const GemmP* d_batch = nullptr, int nb = 1,
-                       int max_m = 0, int max_n = 0) {
+                       int max_m = 0, int max_n = 0, int splitk = 1) {
   constexpr size_t smem = (size_t)STAGES * (BM + BN) * (BK + 4) * sizeof(double);
   static bool attr_dev[64] = {};
   bool& attr_set = attr_dev[ctx->device & 63];
@@ -605,8 +617,8 @@ static int launch_bulk(Ctx* ctx, int flags, const GemmP& p, int tri_keep, const 
     EKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  dim3 grid(cdiv(BATCHED ? max_m : p.m, BM), cdiv(BATCHED ? max_n : p.n, BN), BATCHED ? nb : 1);
-  kern<<<grid, BULK_THREADS, smem, ctx->stream>>>(p, d_batch, flags, tri_keep); EKB_COUNT_LAUNCH(ctx);
+  dim3 grid(cdiv(BATCHED ? max_m : p.m, BM), cdiv(BATCHED ? max_n : p.n, BN), BATCHED ? nb : splitk);
+  kern<<<grid, BULK_THREADS, smem, ctx->stream>>>(p, d_batch, flags, tri_keep, splitk, ctx->splitk_ws); EKB_COUNT_LAUNCH(ctx);
   EKB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -657,11 +669,33 @@ static int launch_shape(Ctx* ctx, int flags, const GemmP& p, const GemmP* d_batc
               : launch_cfg<128, 128, 64, 32, BATCHED, 16, 4>(ctx, flags, p, d_batch, nb, max_m, max_n, tri_keep, splitk);
 }
 
+// Split-K factor for a product the TMA-fed kernel runs: one CTA per SM, so a grid of T tiles costs ceil(T / SMs) full
+// rounds however empty the last one is (250 tiles of the m x 64 panel product at m = 32000: 1.69 -> 2 rounds).  Splitting
+// k by s makes the rounds s times shorter and the count ceil(T s / SMs); the price is the partial-sum pass.  Modelled
+// in seconds (236 GFLOP/s per SM, 4 TB/s for the partial sums), smallest s within 3 % of the best.
+static int bulk_auto_splitk(Ctx* ctx, const GemmP& p) {
+  const int bn = p.n > 64 ? 128 : 64;
+  const double tiles = (double)cdiv(p.m, 128) * cdiv(p.n, bn);
+  const double per_k = 2.0 * 128 * bn / 236e9;  // seconds per unit of k per CTA
+  double best_t = 0.0;
+  int best = 1;
+  for (int s = 1; s <= 8; ++s) {
+    if (s > 1 && (p.k / s < 512 || (double)s * p.m * p.n * 8.0 > 512e6)) break;
+    const double rounds = std::ceil(tiles * s / ctx->num_sms);
+    double t = rounds * per_k * ((double)p.k / s);
+    if (s > 1) t += (double)(s + 2) * p.m * p.n * 8.0 / 4e12 + 3e-6;
+    if (s == 1 || t < 0.97 * best_t) { best_t = t; best = s; }
+  }
+  return best;
+}
+
 int gemm(Ctx* ctx, int flags, const GemmP& p, int tri_keep, int splitk) {
   if (p.m <= 0 || p.n <= 0) return 0;
-  // split-K exists to fill the chip when there are few tiles; with at least one 128-row tile per SM the TMA-fed kernel
-  // (no split-K form) is the better use of them and saves the partial-sum pass
-  if (splitk > 1 && ctx->gemm_bulk != 0 && cdiv(p.m, 128) * (p.n > 64 ? cdiv(p.n, 128) : 1) >= ctx->num_sms) splitk = 1;
+  const bool bulk_shape = ctx->gemm_bulk != 0 && p.m > 64 && p.k >= 64;
+  // products the TMA-fed kernel takes pick their own split (option "gemm_autosplit", default on); otherwise the
+  // caller's request stands, except that with a 128-row tile per SM the unsplit TMA-fed kernel beats a split one
+  if (bulk_shape && tri_keep < 0 && ctx->gemm_autosplit != 0) splitk = bulk_auto_splitk(ctx, p);
+  else if (splitk > 1 && bulk_shape && cdiv(p.m, 128) * (p.n > 64 ? cdiv(p.n, 128) : 1) >= ctx->num_sms) splitk = 1;
   if (splitk > 1) {
     int nkt = cdiv(p.k, 32);
     if (splitk > nkt) splitk = nkt > 0 ? nkt : 1;
@@ -689,11 +723,13 @@ int gemm(Ctx* ctx, int flags, const GemmP& p, int tri_keep, int splitk) {
   // k-depth per CTA (after split-K) decides the pipeline geometry: >= 32 k-tiles of 32 amortise the longer prologue
   const bool deep = p.k / splitk >= 1024;
   // the TMA-fed warp-specialised kernel takes the big-tile products it supports (option "gemm_bulk", default on)
-  const bool bulk_ok = ctx->gemm_bulk != 0 && splitk == 1 && p.m > 64 && p.k >= 64;
+  const bool bulk_ok = bulk_shape && (splitk == 1 || ctx->gemm_autosplit != 0);
   if (bulk_ok && p.n > 64)
-    rc = deep ? launch_bulk<128, 128, 64, 32, 32, 3>(ctx, flags, p, tri_keep) : launch_bulk<128, 128, 64, 32, 16, 4>(ctx, flags, p, tri_keep);
+    rc = deep ? launch_bulk<128, 128, 64, 32, 32, 3>(ctx, flags, p, tri_keep, nullptr, 1, 0, 0, splitk)
+              : launch_bulk<128, 128, 64, 32, 16, 4>(ctx, flags, p, tri_keep, nullptr, 1, 0, 0, splitk);
   else if (bulk_ok)
-    rc = deep ? launch_bulk<128, 64, 32, 32, 32, 3>(ctx, flags, p, tri_keep) : launch_bulk<128, 64, 32, 32, 16, 4>(ctx, flags, p, tri_keep);
+    rc = deep ? launch_bulk<128, 64, 32, 32, 32, 3>(ctx, flags, p, tri_keep, nullptr, 1, 0, 0, splitk)
+              : launch_bulk<128, 64, 32, 32, 16, 4>(ctx, flags, p, tri_keep, nullptr, 1, 0, 0, splitk);
   else
     rc = launch_shape<false>(ctx, flags, p, nullptr, 1, p.m, p.n, tri_keep, splitk, deep);
   if (rc) return rc;

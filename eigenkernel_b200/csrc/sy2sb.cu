@@ -462,8 +462,13 @@ namespace {
 struct OnAuxStream {
   Ctx* ctx;
   cudaStream_t saved;
-  explicit OnAuxStream(Ctx* c) : ctx(c), saved(c->stream) { c->stream = c->aux_stream; }
-  ~OnAuxStream() { ctx->stream = saved; }
+  // the split-K workspace is per stream: products on the two streams may run at the same time
+  explicit OnAuxStream(Ctx* c) : ctx(c), saved(c->stream) { c->stream = c->aux_stream; swap_ws(); }
+  ~OnAuxStream() { ctx->stream = saved; swap_ws(); }
+  void swap_ws() {
+    std::swap(ctx->splitk_ws, ctx->splitk_ws_aux);
+    std::swap(ctx->splitk_ws_bytes, ctx->splitk_ws_aux_bytes);
+  }
 };
 }  // namespace
 

@@ -14,6 +14,9 @@ pytestmark = pytest.mark.gpu
     ("N", "N", 1024, 768, 512), ("N", "T", 1024, 768, 512), ("T", "N", 1024, 768, 512), ("T", "T", 1024, 768, 512),
     ("N", "N", 1100, 700, 500), ("N", "T", 1100, 700, 500), ("T", "N", 1100, 700, 500), ("T", "T", 1100, 700, 500),
     ("N", "N", 2048, 64, 1000), ("T", "N", 64, 2048, 1000), ("N", "T", 2048, 64, 136), ("T", "T", 50, 640, 136),
+    # few tiles, deep k: the TMA-fed kernel splits k (partial sums + reduce pass), ragged tiles / odd m / k tail included
+    ("N", "N", 2048, 64, 4096), ("T", "N", 512, 1024, 4100), ("N", "T", 1100, 700, 3000), ("N", "N", 1001, 64, 2051),
+    ("T", "T", 384, 200, 5000),
 ])
 def test_dgemm_matches_numpy(ctx, ta, tb, m, n, k):
     rng = np.random.default_rng(m * 7 + n * 3 + k)
