@@ -336,6 +336,9 @@ __global__ void __launch_bounds__(32 * (NW + (RING ? 1 : 0)), 1) q2_apply_kernel
       for (int a = 0; a < MI; ++a)
 #pragma unroll
         for (int j = 0; j < NJ; ++j) wacc[a][j][0] = wacc[a][j][1] = 0.0;
+      // (Measured, round 2: issuing the x halves of several accumulators before their y halves, so that no two
+      // consecutive DMMAs accumulate into the same registers, made the walk 2-4 % SLOWER -- back-to-back dependent
+      // DMMAs are not what holds the tensor pipe at ~70 %; the extra live fragments cost more than they gave.)
       {
         const double* yp = Ys + lq * LDY + 2 * lr;
 #pragma unroll
@@ -411,7 +414,10 @@ __global__ void __launch_bounds__(32 * (NW + (RING ? 1 : 0)), 1) q2_apply_kernel
 // 323 / 448 ms for 4 / 7 warps of 16 columns) the time of one CTA is proportional to NJ (4.4 + NW): a lone warp per
 // scheduler is latency-bound, more and thinner warps interleave on the DMMA pipe.
 // NJ = accumulator column tiles per warp: 2 (16 columns) normally; 1 (8 columns per warp) doubles the number of
-// warps when a rank's slab is too narrow to give every scheduler of every SM a warp (multi-GPU column slabs).
+// warps when a rank's slab is too narrow to give every scheduler of every SM a warp (multi-GPU column slabs); 14 such
+// warps + the producer (480 threads, 128 registers) cover the same 112 columns per CTA as 7 warps of 16 and walk them
+// 2.6 % faster (n = 32768: 3.324 -> 3.238 s, round 2) -- far less than the pre-ring model promised: with the ring the
+// fixed cost per block is gone and both shapes sit at ~71 % of the DMMA rate.
 // The choice is returned as NW + 100 * (NJ == 1).
 template <int NW, int NJ>
 static void q2_consider(Ctx* ctx, i64 k, int force_kc, long long* best_cost, int* best_nw) {
@@ -478,6 +484,7 @@ static int q2_launch(Ctx* ctx, i64 n, const double* V2, i64 ldv, const double* T
     q2_consider<4, 1>(ctx, k, ctx->q2_kc, &cost, &nw);
     q2_consider<8, 1>(ctx, k, ctx->q2_kc, &cost, &nw);
     q2_consider<12, 1>(ctx, k, ctx->q2_kc, &cost, &nw);
+    q2_consider<14, 1>(ctx, k, ctx->q2_kc, &cost, &nw);
     const bool al16 = ((uintptr_t)Z & 15) == 0 && (ldz & 1) == 0;
     if (!al16) nw = -4;  // 8-byte global accesses: one generic instantiation
     prof_begin(ctx, PROF_Q2_APPLY, 2.0 * (double)n * (double)n * (double)k);
@@ -491,6 +498,7 @@ static int q2_launch(Ctx* ctx, i64 n, const double* V2, i64 ldv, const double* T
       case 104: ce = q2_apply_launch<B, NBS, 4, true, 1>(ctx, packed, d_off, n, nS, Z, ldz, k); break;
       case 108: ce = q2_apply_launch<B, NBS, 8, true, 1>(ctx, packed, d_off, n, nS, Z, ldz, k); break;
       case 112: ce = q2_apply_launch<B, NBS, 12, true, 1>(ctx, packed, d_off, n, nS, Z, ldz, k); break;
+      case 114: ce = q2_apply_launch<B, NBS, 14, true, 1>(ctx, packed, d_off, n, nS, Z, ldz, k); break;
       default: ce = cudaErrorInvalidValue;
     }
     prof_end(ctx);
