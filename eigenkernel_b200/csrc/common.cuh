@@ -139,6 +139,7 @@ enum GemmFlags {
   GEMM_TA = 1,      // op(A) = A^T
   GEMM_TB = 2,      // op(B) = B^T
   GEMM_SYMA = 4,    // A is symmetric, only elements with (col - row) < 128 are valid (NN only)
+  GEMM_RASTER = 8,  // set by gemm() itself: L2-aware tile order (TMA-fed kernel, deep-k products)
 };
 // tri_keep < 0: full C.  Otherwise only elements with (col - row) < tri_keep are guaranteed to be
 // computed (whole tiles above that region are skipped): 1 = lower triangle, 128 = lower + a 128 band.
