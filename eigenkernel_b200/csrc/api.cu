@@ -193,6 +193,7 @@ int ekb200_set_option(ekb200_ctx* h, const char* key, int64_t value) {
     ctx->prof_flops.clear();
     ctx->prof_family.clear();
     ctx->prof_stage.clear();
+    ctx->prof_shape.clear();
     return 0;
   }
   return -2;

@@ -121,16 +121,18 @@ static int trsm_rec(Ctx* ctx, int kind, i64 m, i64 n, const double* L, i64 ldl, 
     GemmP p;
     p.alpha = 1.0;
     p.beta = 0.0;
+    // IN PLACE (C = the operand being solved for): the leaf has a single tile in the solved dimension (ln <= 64 = one
+    // column tile for RLT, one row tile otherwise) and runs through all of k = ln before its epilogue, so the CTA
+    // that writes a tile of B is the only one that ever read it, and it has read all of it by then (beta = 0: the
+    // epilogue does not read C).  Saves the copy launch every leaf used to need.
     if (kind == TRSM_RLT) {  // X = B * inv^T  (m x ln)
       p.m = (int)m; p.n = (int)ln; p.k = (int)ln;
-      p.A = B; p.lda = ldb; p.B = invd; p.ldb = NB; p.C = tmp; p.ldc = m;
+      p.A = B; p.lda = ldb; p.B = invd; p.ldb = NB; p.C = B; p.ldc = ldb;
       EKB_TRY(gemm(ctx, GEMM_TB, p));
-      EKB_TRY(copy_matrix(ctx, tmp, m, B, ldb, m, ln));
     } else {  // X = inv * B or inv^T * B   (ln x n)
       p.m = (int)ln; p.n = (int)n; p.k = (int)ln;
-      p.A = invd; p.lda = NB; p.B = B; p.ldb = ldb; p.C = tmp; p.ldc = NB;
+      p.A = invd; p.lda = NB; p.B = B; p.ldb = ldb; p.C = B; p.ldc = ldb;
       EKB_TRY(gemm(ctx, kind == TRSM_LLT ? GEMM_TA : 0, p));
-      EKB_TRY(copy_matrix(ctx, tmp, NB, B, ldb, ln, n));
     }
     return 0;
   }

@@ -77,6 +77,8 @@ struct Ctx {
   std::vector<double> prof_flops;         // algorithmic work of that launch (FLOPs, or bytes for HBM-bound families)
   std::vector<int> prof_family;           // kernel family of that launch (ProfFamily)
   std::vector<const char*> prof_stage;    // innermost StageTimer name active at that launch
+  struct ProfShape { int m, n, k, flags, tri, splitk; };
+  std::vector<ProfShape> prof_shape;      // engine GEMMs: the shape of that launch (EKB200_GEMM_TRACE dump, profile_collect)
   const char* cur_stage = "";
   size_t prof_used = 0;
   struct ProfRow { std::string stage; int family; double seconds, work; long long launches; };

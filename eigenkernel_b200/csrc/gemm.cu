@@ -15,6 +15,9 @@
 // (mn = base + lane/4, k = k4 + lane%4):
 //   K-major  (operand contiguous in k in global):  s[mn * (BK+4) + k]
 //   MN-major (operand contiguous in m/n in global): s[k * (BMN+4) + mn]
+#include <cstdio>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace ekb {
@@ -736,6 +739,7 @@ int gemm(Ctx* ctx, int flags, const GemmP& p, int tri_keep, int splitk) {
       elems = (double)p.m * p.n - 0.5 * mn * (mn - 1.0);
     }
     EKB_TRY(prof_begin(ctx, PROF_GEMM, 2.0 * p.k * elems));
+    if (ctx->profile_gemm) ctx->prof_shape.back() = Ctx::ProfShape{p.m, p.n, p.k, flags, tri_keep, splitk};
   }
   // k-depth per CTA (after split-K) decides the pipeline geometry: >= 32 k-tiles of 32 amortise the longer prologue
   const bool deep = p.k / splitk >= 1024;
@@ -774,6 +778,7 @@ int prof_begin(Ctx* ctx, int family, double work) {
   ctx->prof_flops.push_back(work);
   ctx->prof_family.push_back(family);
   ctx->prof_stage.push_back(ctx->cur_stage);
+  ctx->prof_shape.push_back(Ctx::ProfShape{0, 0, 0, 0, 0, 0});
   EKB_CUDA(cudaEventRecord(ctx->prof_events[ctx->prof_used], ctx->stream));
   return 0;
 }
@@ -789,10 +794,20 @@ int profile_collect(Ctx* ctx, double* seconds, double* work, long long* launches
   EKB_CUDA(cudaStreamSynchronize(ctx->stream));
   for (int f = 0; f < PROF_FAMILIES; ++f) { seconds[f] = 0.0; work[f] = 0.0; launches[f] = 0; }
   ctx->prof_table.clear();
+  // EKB200_GEMM_TRACE=<file>: one line per engine GEMM (stage m n k flags tri_keep splitk ms), appended -- the
+  // per-shape view behind the (stage, family) table (scripts/gemm_trace_summary.py)
+  const char* trace_path = getenv("EKB200_GEMM_TRACE");
+  FILE* trace = (trace_path && *trace_path) ? fopen(trace_path, "a") : nullptr;
+  struct Closer { FILE* f; ~Closer() { if (f) fclose(f); } } closer{trace};
   for (size_t q = 0; q + 1 < ctx->prof_used; q += 2) {
     float ms = 0.f;
     EKB_CUDA(cudaEventElapsedTime(&ms, ctx->prof_events[q], ctx->prof_events[q + 1]));
     const int f = ctx->prof_family[q / 2];
+    if (trace && f == PROF_GEMM && q / 2 < ctx->prof_shape.size()) {
+      const Ctx::ProfShape& sh = ctx->prof_shape[q / 2];
+      fprintf(trace, "%s %d %d %d %d %d %d %.6f\n", ctx->prof_stage[q / 2] ? ctx->prof_stage[q / 2] : "-", sh.m, sh.n, sh.k,
+              sh.flags, sh.tri, sh.splitk, (double)ms);
+    }
     seconds[f] += ms * 1e-3;
     work[f] += ctx->prof_flops[q / 2];
     launches[f] += 1;
@@ -812,6 +827,7 @@ int profile_collect(Ctx* ctx, double* seconds, double* work, long long* launches
   ctx->prof_flops.clear();
   ctx->prof_family.clear();
   ctx->prof_stage.clear();
+  ctx->prof_shape.clear();
   return 0;
 }
 
