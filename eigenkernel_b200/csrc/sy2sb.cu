@@ -193,6 +193,7 @@ __global__ void __launch_bounds__(QR_THREADS) panel_qr_kernel(double* __restrict
 // per column.  Cooperative launch for co-residency; same outputs, same operation order per element as the kernel above
 // except for the order of the partial sums.
 constexpr int QRS_MAXROWS = 352;
+constexpr int QRS_MAXG = 160;  // CTAs of the shared-memory panel QR (<= SM count; the launcher falls back above it)
 template <int B>
 __global__ void __launch_bounds__(QR_THREADS, 1) panel_qr_smem_kernel(double* __restrict__ P, i64 ld, int m,
                                                                       double* __restrict__ tau, double* __restrict__ Rout,
@@ -226,10 +227,19 @@ __global__ void __launch_bounds__(QR_THREADS, 1) panel_qr_smem_kernel(double* __
       // partial dots of column j with columns j..B-1 (rows > j), summed over the CTAs in a fixed order
       const double* pp = partial + (size_t)(j & 1) * G * B;
       {
+        // every load of this thread's share in flight at once (one L2 round trip instead of one per 8 CTAs; the sum
+        // keeps its order): G <= QRS_MAXG CTAs, NQ slices
         double sacc = 0.0;
         if (c >= j) {
-#pragma unroll 8
-          for (int t = q; t < G; t += NQ) sacc += __ldcg(pp + t * B + c);
+          constexpr int NT = (QRS_MAXG + NQ - 1) / NQ;
+          double vals[NT];
+#pragma unroll
+          for (int u = 0; u < NT; ++u) {
+            const int t = q + u * NQ;
+            vals[u] = t < G ? __ldcg(pp + t * B + c) : 0.0;
+          }
+#pragma unroll
+          for (int u = 0; u < NT; ++u) sacc += vals[u];
         }
         red[q][c] = sacc;
       }
@@ -401,7 +411,7 @@ static int launch_panel_qr_smem(Ctx* ctx, int b, double* P, i64 ld, int m, doubl
   int G = (m + QR_THREADS - 1) / QR_THREADS;
   if (G > ctx->num_sms) G = ctx->num_sms;
   const int rpc = (m + G - 1) / G;
-  if (rpc > QRS_MAXROWS) return -1;
+  if (rpc > QRS_MAXROWS || G > QRS_MAXG) return -1;
   const size_t smem = (size_t)(rpc | 1) * b * sizeof(double);
   void* args[] = {(void*)&P, (void*)&ld, (void*)&m, (void*)&tau, (void*)&Rout, (void*)&partial, (void*)&rowbuf, (void*)&bar};
   void* kern = b == 64 ? (void*)panel_qr_smem_kernel<64> : (void*)panel_qr_smem_kernel<32>;
