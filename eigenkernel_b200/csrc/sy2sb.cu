@@ -205,6 +205,7 @@ __global__ void __launch_bounds__(QR_THREADS, 1) panel_qr_smem_kernel(double* __
   __shared__ double red[NQ][B];
   __shared__ double g[B];
   __shared__ double wv[B];
+  __shared__ double srow[B];
   __shared__ double s_scal, s_tau;
   const int G = gridDim.x, tid = threadIdx.x;
   const int rpc = (m + G - 1) / G;
@@ -226,7 +227,11 @@ __global__ void __launch_bounds__(QR_THREADS, 1) panel_qr_smem_kernel(double* __
     if (j >= 0) {
       // partial dots of column j with columns j..B-1 (rows > j), summed over the CTAs in a fixed order
       const double* pp = partial + (size_t)(j & 1) * G * B;
+      const double* prow = rowbuf + (j & 1) * B;  // row j of the panel, published by its owner before the barrier
       {
+        // the pivot row travels with the partial dots (same round trip), then lives in shared memory
+        double rowv = 0.0;
+        if (tid < B) rowv = __ldcg(prow + tid);
         // every load of this thread's share in flight at once (one L2 round trip instead of one per 8 CTAs; the sum
         // keeps its order): G <= QRS_MAXG CTAs, NQ slices
         double sacc = 0.0;
@@ -242,6 +247,7 @@ __global__ void __launch_bounds__(QR_THREADS, 1) panel_qr_smem_kernel(double* __
           for (int u = 0; u < NT; ++u) sacc += vals[u];
         }
         red[q][c] = sacc;
+        if (tid < B) srow[tid] = rowv;
       }
       __syncthreads();
       if (tid < B) {
@@ -251,9 +257,8 @@ __global__ void __launch_bounds__(QR_THREADS, 1) panel_qr_smem_kernel(double* __
         g[tid] = sacc;
       }
       __syncthreads();
-      const double* prow = rowbuf + (j & 1) * B;  // row j of the panel, published by its owner before the barrier
       if (tid == 0) {
-        const double alpha = __ldcg(prow + j);
+        const double alpha = srow[j];
         const double xn2 = g[j];
         double beta, t, sc;
         if (xn2 == 0.0) {
@@ -269,7 +274,7 @@ __global__ void __launch_bounds__(QR_THREADS, 1) panel_qr_smem_kernel(double* __
       __syncthreads();
       scal = s_scal; tj = s_tau;
       if (tid < B && tid > j) {
-        const double pjc = __ldcg(prow + tid);
+        const double pjc = srow[tid];
         const double w = pjc + scal * g[tid];
         wv[tid] = tj * w;
         if (blockIdx.x == 0) Rout[tid * B + j] = pjc - tj * w;
