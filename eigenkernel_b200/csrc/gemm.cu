@@ -410,15 +410,7 @@ __global__ void __launch_bounds__(BULK_THREADS, 1) gemm_bulk_kernel(GemmP p0, co
   // rank-128 / rank-512 updates, whose traffic is C, LOSE 2 % with it and keep the plain order.
   constexpr int RASTER = 12;
   int tile_m = blockIdx.x, tile_n = blockIdx.y;
-  if (flags & GEMM_RASTER) {
-    const int gm = gridDim.x, pid = blockIdx.x + gm * blockIdx.y;
-    const int per = RASTER * gridDim.y;
-    const int grp = pid / per, first = grp * RASTER;
-    const int gsz = min(gm - first, RASTER);
-    const int rem = pid - grp * per;
-    tile_m = first + rem % gsz;
-    tile_n = rem / gsz;
-  }
+  if (flags & GEMM_RASTER) gemm_raster_tile(blockIdx.x + gridDim.x * blockIdx.y, gridDim.x, gridDim.y, RASTER, &tile_m, &tile_n);
   const int m0 = tile_m * BM, n0 = tile_n * BN;
   if (m0 >= p.m || n0 >= p.n) return;
   if (tri_keep >= 0 && n0 - (m0 + BM - 1) >= tri_keep) return;
@@ -689,32 +681,12 @@ static int launch_shape(Ctx* ctx, int flags, const GemmP& p, const GemmP* d_batc
               : launch_cfg<128, 128, 64, 32, BATCHED, 16, 4>(ctx, flags, p, d_batch, nb, max_m, max_n, tri_keep, splitk);
 }
 
-// Split-K factor for a product the TMA-fed kernel runs: one CTA per SM, so a grid of T tiles costs ceil(T / SMs) full
-// rounds however empty the last one is (250 tiles of the m x 64 panel product at m = 32000: 1.69 -> 2 rounds).  Splitting
-// k by s makes the rounds s times shorter and the count ceil(T s / SMs); the price is the partial-sum pass.  Modelled
-// in seconds (236 GFLOP/s per SM, 4 TB/s for the partial sums), smallest s within 3 % of the best.
-static int bulk_auto_splitk(Ctx* ctx, const GemmP& p) {
-  const int bn = p.n > 64 ? 128 : 64;
-  const double tiles = (double)cdiv(p.m, 128) * cdiv(p.n, bn);
-  const double per_k = 2.0 * 128 * bn / 236e9;  // seconds per unit of k per CTA
-  double best_t = 0.0;
-  int best = 1;
-  for (int s = 1; s <= 8; ++s) {
-    if (s > 1 && (p.k / s < 512 || (double)s * p.m * p.n * 8.0 > 512e6)) break;
-    const double rounds = std::ceil(tiles * s / ctx->num_sms);
-    double t = rounds * per_k * ((double)p.k / s);
-    if (s > 1) t += (double)(s + 2) * p.m * p.n * 8.0 / 4e12 + 3e-6;
-    if (s == 1 || t < 0.97 * best_t) { best_t = t; best = s; }
-  }
-  return best;
-}
-
 int gemm(Ctx* ctx, int flags, const GemmP& p, int tri_keep, int splitk) {
   if (p.m <= 0 || p.n <= 0) return 0;
   const bool bulk_shape = ctx->gemm_bulk != 0 && p.m > 64 && p.k >= 64;
   // products the TMA-fed kernel takes pick their own split (option "gemm_autosplit", default on); otherwise the
   // caller's request stands, except that with a 128-row tile per SM the unsplit TMA-fed kernel beats a split one
-  if (bulk_shape && tri_keep < 0 && ctx->gemm_autosplit != 0) splitk = bulk_auto_splitk(ctx, p);
+  if (bulk_shape && tri_keep < 0 && ctx->gemm_autosplit != 0) splitk = gemm_autosplit_factor(p.m, p.n, p.k, ctx->num_sms);  // layout.h
   else if (splitk > 1 && bulk_shape && cdiv(p.m, 128) * (p.n > 64 ? cdiv(p.n, 128) : 1) >= ctx->num_sms) splitk = 1;
   if (splitk > 1) {
     int nkt = cdiv(p.k, 32);

@@ -43,6 +43,13 @@ extern "C" long long ekb200_host_cyclic_global_col(long long lc, long long nb, i
   return ekb::cyclic_global_col0(lc, nb, nprocs, r);
 }
 
+extern "C" int ekb200_host_gemm_autosplit(long long m, long long n, long long k, int num_sms) {
+  return ekb::gemm_autosplit_factor(m, n, k, num_sms);
+}
+extern "C" void ekb200_host_gemm_raster_tile(int pid, int gm, int gn, int raster, int* tm, int* tn) {
+  ekb::gemm_raster_tile(pid, gm, gn, raster, tm, tn);
+}
+
 // ---- bisection + inverse iteration (tridiag.cuh), the host run of exactly the code the CUDA kernels execute
 static void tri_setup(long long n, const double* d, const double* e, std::vector<double>& e2, double* gl, double* gu,
                       double* onenrm, double* pivmin) {
