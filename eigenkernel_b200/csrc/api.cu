@@ -174,7 +174,7 @@ int ekb200_set_option(ekb200_ctx* h, const char* key, int64_t value) {
     return 0;
   }
   if (!strcmp(key, "q2_kc")) {
-    if (value != 0 && value != 1004 && value != 1008 && value != 1012 && (value < 64 || value > 128 || value % 16))
+    if (value != 0 && value != 1004 && value != 1008 && value != 1012 && value != 1014 && (value < 64 || value > 128 || value % 16))
       return -3;
     ctx->q2_kc = (int)value;
     return 0;

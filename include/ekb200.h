@@ -46,7 +46,7 @@ int ekb200_set_option(ekb200_ctx* ctx, const char* key, int64_t value); /* "band
                                                                            tuning / experiments (defaults are the measured best):
                                                                            "sb2st_variant", "sb2st_warps", "sb2st_rwarp", "sb2st_cps",
                                                                            "panel_qr_variant", "sy2sb_lookahead", "gemm_bulk",
-                                                                           "stedc_shard", "q2_kc" */
+                                                                           "stedc_shard", "q2_kc", "gemm_autosplit" */
 int ekb200_version(void);
 int ekb200_device_count(void); /* visible CUDA devices (0 when there is none); a rank uses device = local rank */
 
