@@ -203,10 +203,7 @@ __global__ void __launch_bounds__(QR_THREADS, 1) panel_qr_smem_kernel(double* __
   extern __shared__ double ps[];  // ps[c * ldp + i]: column c, local row i
   constexpr int NQ = QR_THREADS / B;
   __shared__ double red[NQ][B];
-  __shared__ double g[B];
-  __shared__ double wv[B];
   __shared__ double srow[B];
-  __shared__ double s_scal, s_tau;
   const int G = gridDim.x, tid = threadIdx.x;
   const int rpc = (m + G - 1) / G;
   const int r0 = blockIdx.x * rpc, r1 = min(m, r0 + rpc);
@@ -223,7 +220,7 @@ __global__ void __launch_bounds__(QR_THREADS, 1) panel_qr_smem_kernel(double* __
   __syncthreads();
 
   for (int j = -1; j < kr; ++j) {
-    double scal = 0.0, tj = 0.0;
+    double scal = 0.0, tj = 0.0, wc_own = 0.0;
     if (j >= 0) {
       // partial dots of column j with columns j..B-1 (rows > j), summed over the CTAs in a fixed order
       const double* pp = partial + (size_t)(j & 1) * G * B;
@@ -250,53 +247,49 @@ __global__ void __launch_bounds__(QR_THREADS, 1) panel_qr_smem_kernel(double* __
         if (tid < B) srow[tid] = rowv;
       }
       __syncthreads();
-      if (tid < B) {
-        double sacc = 0.0;
+      // Every thread derives the reflector's scalars and the w of ITS column from the block-level sums (same values in
+      // every thread: no elected thread, no broadcast round; three block barriers per column instead of six)
+      auto colsum = [&](int col) {
+        double sacc2 = 0.0;
 #pragma unroll
-        for (int t = 0; t < NQ; ++t) sacc += red[t][tid];
-        g[tid] = sacc;
+        for (int t = 0; t < NQ; ++t) sacc2 += red[t][col];
+        return sacc2;
+      };
+      const double alpha = srow[j];
+      const double xn2 = colsum(j);
+      double beta;
+      if (xn2 == 0.0) {
+        beta = alpha; tj = 0.0; scal = 0.0;
+      } else {
+        beta = -copysign(sqrt(alpha * alpha + xn2), alpha);
+        tj = (beta - alpha) / beta;
+        scal = 1.0 / (alpha - beta);
       }
-      __syncthreads();
-      if (tid == 0) {
-        const double alpha = srow[j];
-        const double xn2 = g[j];
-        double beta, t, sc;
-        if (xn2 == 0.0) {
-          beta = alpha; t = 0.0; sc = 0.0;
-        } else {
-          beta = -copysign(sqrt(alpha * alpha + xn2), alpha);
-          t = (beta - alpha) / beta;
-          sc = 1.0 / (alpha - beta);
-        }
-        s_scal = sc; s_tau = t;
-        if (blockIdx.x == 0) { tau[j] = t; Rout[j * B + j] = beta; }
+      const double pjc = srow[c];
+      const double w = pjc + scal * colsum(c);
+      wc_own = tj * w;
+      const int jn1 = j + 1;
+      const double wn = jn1 < B ? tj * (srow[jn1] + scal * colsum(jn1)) : 0.0;
+      if (blockIdx.x == 0 && q == 0) {
+        if (c == j) { tau[j] = tj; Rout[j * B + j] = beta; }
+        else if (c > j) Rout[c * B + j] = pjc - tj * w;
       }
-      __syncthreads();
-      scal = s_scal; tj = s_tau;
-      if (tid < B && tid > j) {
-        const double pjc = srow[tid];
-        const double w = pjc + scal * g[tid];
-        wv[tid] = tj * w;
-        if (blockIdx.x == 0) Rout[tid * B + j] = pjc - tj * w;
-      }
-      // v_j: scale column j below the pivot (the reflector, stored in place)
+      // v_j: scale column j below the pivot (the reflector, stored in place), and apply it to the next pivot column
+      // at once (every thread of the main pass reads that column's UPDATED values)
       for (int i = tid; i < rows; i += QR_THREADS)
-        if (r0 + i > j) ps[j * ldp + i] *= scal;
+        if (r0 + i > j) {
+          const double v = ps[j * ldp + i] * scal;
+          ps[j * ldp + i] = v;
+          if (jn1 < B) ps[jn1 * ldp + i] -= wn * v;
+        }
       __syncthreads();
     }
     const int jn = j + 1;  // next pivot column
     if (jn < B) {
-      // the next pivot column first (every thread of the main pass reads its UPDATED values) ...
-      if (j >= 0) {
-        const double wn = wv[jn];
-        for (int i = tid; i < rows; i += QR_THREADS)
-          if (r0 + i > j) ps[jn * ldp + i] -= wn * ps[j * ldp + i];
-        __syncthreads();
-      }
-      // ... then reflector j on the other columns, fused with the dots of column jn against columns >= jn
+      // reflector j on the other columns, fused with the dots of column jn against columns >= jn
       double acc = 0.0;
       if (c >= jn) {
-        const double wc = (j >= 0 && c > jn) ? wv[c] : 0.0;
+        const double wc = (j >= 0 && c > jn) ? wc_own : 0.0;
         const double* vj = ps + (j >= 0 ? j : 0) * ldp;
         const double* pn = ps + jn * ldp;
         double* pc = ps + c * ldp;
