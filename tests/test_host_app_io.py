@@ -102,6 +102,16 @@ def test_cabi_library_exports_every_declared_symbol():
     assert lib.ekb200_version() >= 100
 
 
+def test_every_option_key_is_documented_in_the_header():
+    """ekb200_set_option's keys (csrc/api.cu) and the list in include/ekb200.h stay in step, both ways."""
+    api = open(os.path.join(ROOT, "eigenkernel_b200", "csrc", "api.cu")).read()
+    accepted = set(re.findall(r'strcmp\(key, "([a-z0-9_]+)"\)', api))
+    hdr = open(os.path.join(ROOT, "include", "ekb200.h")).read()
+    decl = hdr[hdr.index("int ekb200_set_option("):hdr.index("int ekb200_version(")]
+    documented = set(re.findall(r'"([a-z0-9_]+)"', decl))
+    assert accepted == documented, (sorted(accepted - documented), sorted(documented - accepted))
+
+
 def test_product_path_fails_loudly_without_gpu():
     import torch
     if torch.cuda.is_available():
